@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py — decoded symbols/s of the fused ViterbiNet detection path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on):
+  ViterbiNet, memory_length 4 (16 states), 2^20 synthetic ISI-AWGN frames x 120 symbols per GPU,
+  one SNR point of the 7..12 dB sweep per rank (weak scaling, no data-path collective; the
+  [bit errors, frame errors, bits, frames] counters are all-reduced over NCCL once per step).
+A "step" = one pass of the fused priors-MLP + ACS + decision kernel over the rank's batch with the
+decoded words written as fp32 [B,T] (the reference's dtype) and BER/FER counted in-kernel.
+
+One JSON line on stdout (rank 0).  `value` = device-resident throughput, `e2e` = the same metric
+through the C-ABI host-buffer entry point (pinned host y in, decoded words out, copies timed).
+`--impl reference` times the torch-CPU port of the reference's VNETDetector forward
+(oracle/torch_port.py) on the host cores, rank 0 only.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MEMORY_LENGTH = 4
+N_STATES = 16
+T = 120
+FRAMES = 1 << 20
+SNR_SWEEP = [7, 8, 9, 10, 11, 12]          # plotter_main.py:117-122
+GAMMA = 0.2
+FLOP_PER_SYMBOL = 2 * (100 + 5000 + 50 * N_STATES) + 2 * N_STATES     # 11 832
+HBM_BYTES_PER_SYMBOL = 8                                              # fp32 y in, fp32 decoded out
+METRIC = 'decoded symbols/sec, ViterbiNet L=4 (16-state)'
+UNIT = 'symbols/s'
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+def make_weights(torch, device):
+    """Random-init weights of the reference architecture (vnet_detector.py:27-33), seed 0."""
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(1, 100), torch.nn.Sigmoid(), torch.nn.Linear(100, 50),
+                              torch.nn.ReLU(), torch.nn.Linear(50, N_STATES))
+    return [p.detach().to(device).contiguous() for p in net.parameters()]
+
+
+def synth_frames(torch, device, frames, snr_db, seed):
+    """bits -> pad L zeros -> BPSK -> ISI (time_decay taps, gamma 0.2) -> AWGN; Appendix A of SURVEY.md."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    L = MEMORY_LENGTH
+    bits = torch.randint(0, 2, (frames, T), generator=g, device=device, dtype=torch.int8)
+    s = torch.ones((frames, T + L), device=device)
+    s[:, :T] = 1.0 - 2.0 * bits.float()
+    h = torch.exp(-GAMMA * torch.arange(L, device=device, dtype=torch.float32))
+    y = torch.zeros((frames, T), device=device)
+    for i in range(L):
+        y += h[L - 1 - i] * s[:, i:i + T]
+    y += (10 ** (-snr_db / 20.0)) * torch.randn((frames, T), generator=g, device=device)
+    return bits.float().contiguous(), y.contiguous()
+
+
+class ClockSampler:
+    FIELDS = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix='mvn_clocks_', suffix='.csv')
+            os.close(fd)
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.FIELDS}', '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(self.index)], stdout=open(self.path, 'w'),
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(',')]
+                if len(p) < 8:
+                    continue
+                try:
+                    sm.append(float(p[1]))
+                    mx.append(float(p[2]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, p[4:8]):
+                    if v.lower().startswith('active'):
+                        reasons.add(n)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_port_rate(frames_per_chunk, chunks, weights_np, y_np, reps=1):
+    """symbols/s of the torch-CPU port of VNETDetector.forward(y,'val') on all host threads."""
+    import torch
+    from oracle import torch_port as tp
+    torch.set_num_threads(os.cpu_count() or 1)
+    net = tp.make_net(N_STATES)
+    tp.load_weights(net, weights_np)
+    y = torch.as_tensor(y_np)
+    best = None
+    with torch.no_grad():
+        tp.vnet_forward_val(net, y[:min(1024, y.shape[0])], T)            # warm-up
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            for c in range(chunks):
+                tp.vnet_forward_val(net, y[c * frames_per_chunk:(c + 1) * frames_per_chunk], T)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return frames_per_chunk * chunks * T / best, best
+
+
+def run_reference(args, rank):
+    """Reference arm: the reference's CPU implementation (torch port, all host threads), rank 0 only."""
+    if rank != 0:
+        return 0
+    import numpy as np
+    import torch
+    torch.manual_seed(0)
+    w = [p.numpy() for p in make_weights(torch, 'cpu')]
+    chunk, chunks = 16384, 2                        # bounded sample per step: 32 768 frames x 120
+    _, y = synth_frames(torch, 'cpu', chunk * chunks, SNR_SWEEP[3], 3450002)
+    y_np = y.numpy()
+    for _ in range(max(args.warmup, 1)):
+        cpu_port_rate(chunk, 1, w, y_np)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_port_rate(chunk, chunks, w, y_np)
+    dt = time.perf_counter() - t0
+    value = args.steps * chunk * chunks * T / dt
+    cores = torch.get_num_threads()
+    sample = f'{chunk * chunks} frames x {T} symbols per step (chunks of {chunk}), torch {torch.__version__} CPU'
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(args.gpus),
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(n_gpus):
+    return {'workload': f'fused ViterbiNet priors-MLP+ACS+decision, memory_length 4 (16 states), {FRAMES} frames x '
+                        f'{T} symbols per GPU, synthetic ISI-AWGN (time_decay taps, gamma {GAMMA}), SNR sweep '
+                        f'{SNR_SWEEP[0]}..{SNR_SWEEP[-1]} dB sharded one point per rank, random-init weights',
+            'frames_per_gpu': FRAMES, 'block_length': T, 'n_states': N_STATES, 'out_dtype': 'f32 [B,T]',
+            'l2': 'inputs (503 MB y + 503 MB targets per step) are larger than the 126 MB L2; no flush needed',
+            'parallelism': f'frames/SNR points sharded over {n_gpus} GPU(s), counters all-reduced'}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--frames', type=int, default=FRAMES, help=argparse.SUPPRESS)
+    ap.add_argument('--no-cpu-baseline', action='store_true', help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    rank, world, local = env_int('RANK', 0), env_int('WORLD_SIZE', 1), env_int('LOCAL_RANK', 0)
+    if args.impl == 'reference':
+        return run_reference(args, rank)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import meta_viterbinet_b200 as mvn
+    from meta_viterbinet_b200 import _lib
+
+    assert torch.cuda.is_available(), 'bench.py needs a GPU (there is no CPU fallback); use --impl reference for the CPU arm'
+    warmup = max(args.warmup, 3)
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=device)
+    frames = args.frames
+    snr = SNR_SWEEP[rank % len(SNR_SWEEP)]
+    weights = make_weights(torch, device)
+    bits, y = synth_frames(torch, device, frames, snr, 3450002 + rank)       # noise_seed of config.yaml:40
+    decoded = torch.empty_like(y)
+    counters = torch.zeros(4, dtype=torch.int64, device=device)
+    lib = _lib.load()
+    stream = _lib.stream()
+    wp = [_lib.ptr(w) for w in weights]
+
+    def step():
+        _lib.check(lib.mvn_vnet_decode(_lib.ptr(y), frames, T, MEMORY_LENGTH, T, *wp, 0, _lib.ptr(decoded), None,
+                                       _lib.ptr(bits), T, 0, _lib.ptr(counters), stream))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # measured FP32 peak (register-only FMA micro-benchmark) before the clock sampler starts
+    peak_ffma, _ = _lib.fp32_peak(0, 2048)
+    peak_ffma2, _ = _lib.fp32_peak(1, 2048)
+    peak_fma = max(peak_ffma, peak_ffma2)
+
+    for _ in range(warmup):
+        step()
+        if world > 1:
+            dist.all_reduce(counters.clone())
+    barrier()
+    counters.zero_()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    _lib.launch_count(reset=True)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    total = counters
+    for k in range(args.steps):
+        ev[k][0].record()
+        step()
+        ev[k][1].record()
+        if world > 1:
+            total = counters.clone()
+            dist.all_reduce(total)                 # the only collective: 4 x int64 per step
+    e1.record()
+    barrier()
+    launches = _lib.launch_count()
+    ms_total = e0.elapsed_time(e1)
+    kern_ms = [a.elapsed_time(b) for a, b in ev]
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    symbols_per_step = frames * T * world
+    value = symbols_per_step * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e through the host-buffer C-ABI call: pinned y in, decoded words out
+    y_host = y.cpu().pin_memory()
+    out_host = torch.empty_like(y_host).pin_memory()
+    ctx = ctypes.c_void_p()
+    _lib.check(lib.mvn_ctx_create(ctypes.byref(ctx), local, 1 << 16, T, MEMORY_LENGTH))
+    w_host = [w.cpu().contiguous() for w in weights]
+    _lib.check(lib.mvn_ctx_set_vnet_weights_host(ctx, *[ctypes.c_void_p(w.data_ptr()) for w in w_host]))
+
+    def e2e_step():
+        _lib.check(lib.mvn_ctx_vnet_decode_host(ctx, ctypes.c_void_p(y_host.data_ptr()), frames, T, T, 0,
+                                                ctypes.c_void_p(out_host.data_ptr())))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_value = symbols_per_step * args.steps / float(dt.item())
+    lib.mvn_ctx_destroy(ctx)
+    e2e_ok = bool(torch.equal(out_host[:4096], decoded[:4096].cpu()))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- supplementary: classical VA kernel on the same frames (configs[1]), outside the timed region
+    from meta_viterbinet_b200.channel_taps import channel_taps, state_priors_table
+    table = torch.as_tensor(state_priors_table(channel_taps(MEMORY_LENGTH, GAMMA, 'time_decay'), MEMORY_LENGTH)).to(device)
+    va0, va1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    mvn.ops.va_decode(y, table)
+    torch.cuda.synchronize()
+    va0.record()
+    for _ in range(5):
+        _lib.check(lib.mvn_va_decode(_lib.ptr(y), frames, T, MEMORY_LENGTH, T, _lib.ptr(table), 1, 0,
+                                     _lib.ptr(decoded), None, 0, 0, None, stream))
+    va1.record()
+    torch.cuda.synchronize()
+    va_ms = va0.elapsed_time(va1) / 5
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    hbm_peak = peaks.get('hbm_gbs', 6650.0)
+    k_ms = statistics.mean(kern_ms)
+    achieved_tflops = FLOP_PER_SYMBOL * frames * T / (k_ms * 1e-3) / 1e12
+    peak_tflops = 2 * peak_fma / 1e12
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get('vnet_decode_bytes_per_launch')
+    except Exception:
+        pass
+    roofline = {'bound': 'fp32', 'achieved': achieved_tflops, 'peak': peak_tflops, 'unit': 'TFLOP/s',
+                'frac': achieved_tflops / peak_tflops, 'traffic': traffic,
+                'kernel': 'vnet_decode_kernel<4>', 'kernel_ms': k_ms,
+                'flop_per_symbol': FLOP_PER_SYMBOL,
+                'peak_source': 'measured live: register-only FMA micro-benchmark mvn_fp32_peak '
+                               f'(FFMA {2 * peak_ffma / 1e12:.1f}, FFMA2 {2 * peak_ffma2 / 1e12:.1f} TFLOP/s); '
+                               'MEASURED_PEAKS.json has no FP32 entry; nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5',
+                'hbm': {'achieved': HBM_BYTES_PER_SYMBOL * frames * T / (k_ms * 1e-3) / 1e9, 'peak': hbm_peak,
+                        'unit': 'GB/s', 'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback'}}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        chunk, chunks = 16384, 6
+        w_np = [w.cpu().numpy() for w in weights]
+        rate, secs = cpu_port_rate(chunk, chunks, w_np, y_host[:chunk * chunks].numpy(), reps=2)
+        cpu_baseline = {'value': rate, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+                        'sample': f'first {chunk * chunks} frames x {T} symbols of the same batch, chunks of {chunk}, '
+                                  f'best of 2 ({secs:.1f} s), oracle/torch_port.py (op-for-op port of '
+                                  'VNETDetector.forward val), torch ' + torch.__version__}
+
+    be, fe, nb, nf = [int(v) for v in total.tolist()]
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': warmup,
+            'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(world),
+            'roofline': roofline, 'cpu_baseline': cpu_baseline,
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': frames * T * 4 * world,
+                    'd2h_bytes_per_step': frames * T * 4 * world, 'matches_device_path': e2e_ok,
+                    'api': 'mvn_ctx_vnet_decode_host (pinned host buffers, 65536-frame chunks, 2 streams)'},
+            'gpu_launches': launches, 'clocks': clocks,
+            'ber': {'bit_errors': be, 'frame_errors': fe, 'bits': nb, 'frames': nf,
+                    'note': 'untrained (random-init) weights: BER is ~0.5 by construction'},
+            'va_kernel': {'symbols_per_s': frames * T / (va_ms * 1e-3), 'ms': va_ms,
+                          'hbm_gbs': HBM_BYTES_PER_SYMBOL * frames * T / (va_ms * 1e-3) / 1e9,
+                          'workload': f'classical VA, 16 states, {frames} frames x {T}, 1 GPU, bit-exact path'}}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -1,0 +1,380 @@
+// a2 / a3 / a5 — ACS stage, stage loop on a cost tensor, and the fused full-CSI Viterbi.
+// Reference semantics: python_code/utils/trellis_utils.py:16-30, detectors/VA/va_detector.py:52-98.
+#include <algorithm>
+#include <type_traits>
+
+#include "mvn_common.cuh"
+
+namespace mvn {
+
+// =====================================================================================
+// a2: one stage on [B,S] tensors (drop-in for acs_block; not a hot kernel)
+// =====================================================================================
+__global__ void acs_block_kernel(const float *__restrict__ in_prob, const float *__restrict__ llrs,
+                                 int llrs_stride, int64_t B, int S, float *__restrict__ out_prob,
+                                 int64_t *__restrict__ out_idx) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= B * S) return;
+    const int64_t b = i / S;
+    const int j = int(i % S);
+    const int s0 = (2 * j) % S, s1 = (2 * j + 1) % S;
+    const float l0 = llrs_stride == 1 ? llrs[b] : llrs[b * llrs_stride + s0];
+    const float l1 = llrs_stride == 1 ? llrs[b] : llrs[b * llrs_stride + s1];
+    const float a = in_prob[b * S + s0] + l0;
+    const float c = in_prob[b * S + s1] + l1;
+    out_prob[i] = fminf(a, c);
+    if (out_idx) out_idx[i] = (c < a) ? 1 : 0;
+}
+
+// =====================================================================================
+// a3: stage loop on cost[B,T,S].  HBM-bound: S*4 bytes in, 4 bytes out per symbol.
+// One lane per frame; the warp stages [32 frames x 32 floats] tiles of the [B, T*S] matrix.
+// =====================================================================================
+struct AcsParams {
+    const float *cost;
+    int64_t B;
+    int T, n_stages;
+    int out_format;
+    void *decoded;
+    float *final_pm;
+    uint32_t *survivors;
+    int64_t n_warp_tiles;
+};
+
+template <int L>
+using TrellisFor = typename std::conditional<(L <= 5), RegTrellis<L>, SmemTrellis<L>>::type;
+
+template <int L, int NT>
+__global__ void __launch_bounds__(NT) acs_decode_kernel(AcsParams p) {
+    using D = TrellisDims<L>;
+    constexpr int S = D::S, H = D::H, C = D::C, NCH = D::NCH;
+    constexpr int WARPS = NT / 32;
+    constexpr int SW = (H + 31) / 32;  // survivor words per stage
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *tile = smem + warp * kTileFloats;
+    const float *row = tile + lane * kTileLd;
+
+    TrellisFor<L> tr;
+    if constexpr (L > 5) tr.init(smem + WARPS * kTileFloats, NT, threadIdx.x);
+
+    const int64_t ld = int64_t(p.T) * S;
+    const bool vec_in = is_vec_ok(p.cost, ld, ld);
+    const bool vec_out = p.out_format == MVN_OUT_F32 && is_vec_ok(p.decoded, p.T, p.T);
+    const int n_words = (p.T + 31) / 32;
+
+    for (int64_t wt = int64_t(blockIdx.x) * WARPS + warp; wt < p.n_warp_tiles; wt += int64_t(gridDim.x) * WARPS) {
+        const int64_t row0 = wt * 32;
+        const int64_t b = row0 + lane;
+        tr.reset();
+        for (int t0 = 0; t0 < p.T; t0 += 32) {
+            uint32_t bits = 0;
+            const int t_end = min(32, p.n_stages - t0);
+            int tt = 0;
+            while (tt < t_end) {
+                if constexpr (S <= 32) {
+                    constexpr int SPT = 32 / S;  // stages per staged tile
+                    warp_load_tile(p.cost, p.B, ld, ld, row0, int64_t(t0 + tt) * S, tile, lane, vec_in);
+#pragma unroll
+                    for (int u = 0; u < SPT; u++) {
+                        if (tt < t_end) {
+                            bits |= tr.decide() << tt;
+                            float c0[C];
+#pragma unroll
+                            for (int i = 0; i < C; i++) c0[i] = row[u * S + i];
+                            uint32_t sv = tr.template step_chunk<0>(c0);
+                            if constexpr (NCH == 2) {
+                                float c1[C];
+#pragma unroll
+                                for (int i = 0; i < C; i++) c1[i] = row[u * S + C + i];
+                                sv |= tr.template step_chunk<1>(c1) << (C / 2);
+                            }
+                            tr.commit();
+                            if (p.survivors && b < p.B) p.survivors[(b * p.n_stages + t0 + tt) * SW] = sv;
+                            tt++;
+                        }
+                    }
+                    __syncwarp();
+                } else {
+                    constexpr int TPS = S / 32;  // staged tiles per stage
+                    bits |= tr.decide() << tt;
+                    uint32_t sv = 0;
+                    for (int k = 0; k < TPS; k++) {
+                        warp_load_tile(p.cost, p.B, ld, ld, row0, int64_t(t0 + tt) * S + 32 * k, tile, lane, vec_in);
+#pragma unroll
+                        for (int u = 0; u < 2; u++) {
+                            float cc[C];
+#pragma unroll
+                            for (int i = 0; i < C; i++) cc[i] = row[u * C + i];
+                            const int c = 2 * k + u;
+                            const uint32_t s8 = tr.step_chunk_rt(c, cc);
+                            sv |= s8 << ((c * 8) & 31);
+                            if ((c & 3) == 3 || c == NCH - 1) {
+                                if (p.survivors && b < p.B)
+                                    p.survivors[(b * p.n_stages + t0 + tt) * SW + (c * 8) / 32] = sv;
+                                sv = 0;
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    tr.commit();
+                    tt++;
+                }
+            }
+            if (p.decoded) {
+                if (p.out_format == MVN_OUT_F32)
+                    warp_store_bits_f32(static_cast<float *>(p.decoded), p.B, p.T, p.T, row0, t0, bits, lane, vec_out);
+                else if (b < p.B)
+                    static_cast<uint32_t *>(p.decoded)[b * n_words + t0 / 32] = bits;
+            }
+        }
+        if (p.final_pm && b < p.B) {
+            for (int h = 0; h < H; h++) {
+                const float v = tr.metric(h);
+                p.final_pm[b * S + h] = v;
+                if (S > 1) p.final_pm[b * S + h + H] = v;
+            }
+        }
+    }
+}
+
+// =====================================================================================
+// a5+a3 fused: y[B,T] + state_priors[n_h,S] -> bits.  cost = (y-sp)^2/2 - ln sqrt(2 pi) in
+// separately rounded fp32 ops (no contraction of d*d into the following op: the halving is exact,
+// so fma(d*d, 0.5, -c) with d*d rounded first reproduces torch's three roundings bit for bit).
+// =====================================================================================
+struct VaParams {
+    const float *y;
+    int64_t B;
+    int T, n_stages;
+    const float *sp;  // [n_h, S]
+    int n_h;
+    int out_format;
+    void *decoded;
+    const float *target;
+    int target_T, pilot_period;
+    unsigned long long *counters;
+    int64_t n_warp_tiles;
+};
+
+__device__ __forceinline__ float va_cost(float y, float sp) {
+    const float d = __fsub_rn(y, sp);
+    const float sq = __fmul_rn(d, d);
+    return __fmaf_rn(sq, 0.5f, -kLogSqrt2Pi);
+}
+
+template <int L, int NT>
+__global__ void __launch_bounds__(NT) va_decode_kernel(VaParams p) {
+    using D = TrellisDims<L>;
+    constexpr int S = D::S, C = D::C, NCH = D::NCH;
+    constexpr int WARPS = NT / 32;
+    constexpr bool SP_REGS = (S <= 32);
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *tile = smem + warp * (2 * kTileFloats);
+    float *ttile = tile + kTileFloats;
+    const float *row = tile + lane * kTileLd;
+
+    TrellisFor<L> tr;
+    if constexpr (L > 5) tr.init(smem + WARPS * 2 * kTileFloats, NT, threadIdx.x);
+
+    const bool vec_in = is_vec_ok(p.y, p.T, p.T);
+    const bool vec_out = p.out_format == MVN_OUT_F32 && is_vec_ok(p.decoded, p.T, p.T);
+    const bool vec_tgt = p.target && is_vec_ok(p.target, p.target_T, p.target_T);
+    const int n_words = (p.T + 31) / 32;
+    ErrAcc acc;
+
+    for (int64_t wt = int64_t(blockIdx.x) * WARPS + warp; wt < p.n_warp_tiles; wt += int64_t(gridDim.x) * WARPS) {
+        const int64_t row0 = wt * 32;
+        const int64_t b = row0 + lane;
+        const float *sp_row = p.sp + int64_t((b < p.B ? b : 0) % p.n_h) * S;
+        float sp[SP_REGS ? S : 1];
+        if constexpr (SP_REGS) {
+#pragma unroll
+            for (int s = 0; s < S; s++) sp[s] = __ldg(sp_row + s);
+        }
+        tr.reset();
+        unsigned frame_bit_errs = 0;
+        for (int t0 = 0; t0 < p.T; t0 += 32) {
+            uint32_t bits = 0;
+            const int t_end = min(32, p.n_stages - t0);
+            if (t_end > 0) {
+                warp_load_tile(p.y, p.B, p.T, p.T, row0, t0, tile, lane, vec_in);
+                for (int tt = 0; tt < t_end; tt++) {
+                    const float yv = row[tt];
+                    bits |= tr.decide() << tt;
+                    if constexpr (SP_REGS) {
+                        float c0[C];
+#pragma unroll
+                        for (int i = 0; i < C; i++) c0[i] = va_cost(yv, sp[i]);
+                        tr.template step_chunk<0>(c0);
+                        if constexpr (NCH == 2) {
+                            float c1[C];
+#pragma unroll
+                            for (int i = 0; i < C; i++) c1[i] = va_cost(yv, sp[C + i]);
+                            tr.template step_chunk<1>(c1);
+                        }
+                    } else {
+                        for (int c = 0; c < NCH; c++) {
+                            float cc[C];
+#pragma unroll
+                            for (int i = 0; i < C; i += 4) {
+                                const float4 s4 = __ldg(reinterpret_cast<const float4 *>(sp_row + c * C + i));
+                                cc[i] = va_cost(yv, s4.x);
+                                cc[i + 1] = va_cost(yv, s4.y);
+                                cc[i + 2] = va_cost(yv, s4.z);
+                                cc[i + 3] = va_cost(yv, s4.w);
+                            }
+                            tr.step_chunk_rt(c, cc);
+                        }
+                    }
+                    tr.commit();
+                }
+                __syncwarp();
+            }
+            if (p.decoded) {
+                if (p.out_format == MVN_OUT_F32)
+                    warp_store_bits_f32(static_cast<float *>(p.decoded), p.B, p.T, p.T, row0, t0, bits, lane, vec_out);
+                else if (b < p.B)
+                    static_cast<uint32_t *>(p.decoded)[b * n_words + t0 / 32] = bits;
+            }
+            if (p.target && t0 < p.target_T) {
+                warp_load_tile(p.target, p.B, p.target_T, p.target_T, row0, t0, ttile, lane, vec_tgt);
+                frame_bit_errs += tile_bit_errors(ttile + lane * kTileLd, bits, p.target_T - t0);
+                __syncwarp();
+            }
+        }
+        if (p.target) {
+            const bool counted = b < p.B && !(p.pilot_period > 0 && b % p.pilot_period == 0);
+            if (counted) {
+                acc.bit_errs += frame_bit_errs;
+                acc.frame_errs += frame_bit_errs ? 1u : 0u;
+                acc.bits += unsigned(p.target_T);
+                acc.frames += 1u;
+            }
+            acc.flush(p.counters);
+        }
+    }
+}
+
+// =====================================================================================
+// host wrappers
+// =====================================================================================
+template <int L>
+static int launch_acs(const AcsParams &p, cudaStream_t st) {
+    constexpr int NT = (L <= 5) ? 256 : 128;
+    size_t smem = size_t(NT / 32) * kTileFloats * sizeof(float);
+    if (L > 5) smem += SmemTrellis<L>::bytes(NT);
+    auto kern = acs_decode_kernel<L, NT>;
+    MVN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    int per_sm = 1;
+    MVN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t need = (p.n_warp_tiles + NT / 32 - 1) / (NT / 32);
+    const int grid = int(std::min<int64_t>(need, int64_t(sm_count()) * per_sm));
+    kern<<<grid, NT, smem, st>>>(p);
+    note_launch();
+    MVN_CUDA(cudaGetLastError());
+    return MVN_OK;
+}
+
+template <int L>
+static int launch_va(const VaParams &p, cudaStream_t st) {
+    constexpr int NT = (L <= 5) ? 256 : 128;
+    size_t smem = size_t(NT / 32) * 2 * kTileFloats * sizeof(float);
+    if (L > 5) smem += SmemTrellis<L>::bytes(NT);
+    auto kern = va_decode_kernel<L, NT>;
+    MVN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    int per_sm = 1;
+    MVN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t need = (p.n_warp_tiles + NT / 32 - 1) / (NT / 32);
+    const int grid = int(std::min<int64_t>(need, int64_t(sm_count()) * per_sm));
+    kern<<<grid, NT, smem, st>>>(p);
+    note_launch();
+    MVN_CUDA(cudaGetLastError());
+    return MVN_OK;
+}
+
+#define MVN_DISPATCH_L(L, FN, ...)                                   \
+    switch (L) {                                                     \
+        case 1: return FN<1>(__VA_ARGS__);                           \
+        case 2: return FN<2>(__VA_ARGS__);                           \
+        case 3: return FN<3>(__VA_ARGS__);                           \
+        case 4: return FN<4>(__VA_ARGS__);                           \
+        case 5: return FN<5>(__VA_ARGS__);                           \
+        case 6: return FN<6>(__VA_ARGS__);                           \
+        case 7: return FN<7>(__VA_ARGS__);                           \
+        case 8: return FN<8>(__VA_ARGS__);                           \
+        default: set_error("memory_length %d outside [1,8]", L);     \
+                 return MVN_ERR_ARG;                                 \
+    }
+
+int acs_decode_impl(const AcsParams &p, int L, cudaStream_t st) { MVN_DISPATCH_L(L, launch_acs, p, st) }
+int va_decode_impl(const VaParams &p, int L, cudaStream_t st) { MVN_DISPATCH_L(L, launch_va, p, st) }
+
+}  // namespace mvn
+
+using namespace mvn;
+
+extern "C" int mvn_acs_block(const float *in_prob, const float *llrs, int llrs_stride, int64_t B, int L,
+                             float *out_prob, int64_t *out_idx, void *stream) {
+    if (!in_prob || !llrs || !out_prob || L < 1 || L > 8 || B < 0) {
+        set_error("mvn_acs_block: bad argument");
+        return MVN_ERR_ARG;
+    }
+    const int S = 1 << L;
+    if (llrs_stride != 1 && llrs_stride != S) {
+        set_error("mvn_acs_block: llrs_stride must be 1 or n_states");
+        return MVN_ERR_ARG;
+    }
+    if (B == 0) return MVN_OK;
+    const int64_t n = B * S;
+    acs_block_kernel<<<unsigned((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        in_prob, llrs, llrs_stride, B, S, out_prob, out_idx);
+    note_launch();
+    MVN_CUDA(cudaGetLastError());
+    return MVN_OK;
+}
+
+extern "C" int mvn_acs_decode(const float *cost, int64_t B, int T, int L, int n_stages, int out_format,
+                              void *decoded, float *final_pm, uint32_t *survivors, void *stream) {
+    if (L < 1 || L > 8) {
+        set_error("memory_length %d outside [1,8]", L);
+        return MVN_ERR_ARG;
+    }
+    if (B < 0 || T < 0 || n_stages < 0 || n_stages > T || (B > 0 && T > 0 && !cost) ||
+        (out_format != MVN_OUT_F32 && out_format != MVN_OUT_BITS)) {
+        set_error("mvn_acs_decode: bad argument (B=%lld T=%d n_stages=%d)", (long long)B, T, n_stages);
+        return MVN_ERR_ARG;
+    }
+    if (B == 0 || T == 0) return MVN_OK;
+    AcsParams p{cost, B, T, n_stages, out_format, decoded, final_pm, survivors, (B + 31) / 32};
+    return acs_decode_impl(p, L, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mvn_va_decode(const float *y, int64_t B, int T, int L, int n_stages, const float *state_priors,
+                             int n_h, int out_format, void *decoded, const float *target, int target_T,
+                             int pilot_period, uint64_t *counters, void *stream) {
+    if (L < 1 || L > 8) {
+        set_error("memory_length %d outside [1,8]", L);
+        return MVN_ERR_ARG;
+    }
+    if (B < 0 || T < 0 || n_stages < 0 || n_stages > T || !state_priors || n_h < 1 || (B > 0 && T > 0 && !y) ||
+        (out_format != MVN_OUT_F32 && out_format != MVN_OUT_BITS)) {
+        set_error("mvn_va_decode: bad argument (B=%lld T=%d n_stages=%d n_h=%d)", (long long)B, T, n_stages, n_h);
+        return MVN_ERR_ARG;
+    }
+    if (B % n_h != 0) {  // the reference's tiling of the table fails to broadcast (va_detector.py:64-66)
+        set_error("mvn_va_decode: batch %lld is not a multiple of the %d tap blocks", (long long)B, n_h);
+        return MVN_ERR_ARG;
+    }
+    if (target && (!counters || target_T < 1 || target_T > T)) {
+        set_error("mvn_va_decode: target needs counters and 1 <= target_T <= T");
+        return MVN_ERR_ARG;
+    }
+    if (B == 0 || T == 0) return MVN_OK;
+    VaParams p{y, B, T, n_stages, state_priors, n_h, out_format, decoded, target, target_T, pilot_period,
+               reinterpret_cast<unsigned long long *>(counters), (B + 31) / 32};
+    return va_decode_impl(p, L, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,257 @@
+// Common device/host helpers for the sm_100a detection kernels.
+//
+// Thread mapping used by every decode kernel (DESIGN.md "thread owns frames"):
+//   one LANE owns one frame (or M frames) for its whole length; the S/2 distinct path
+//   metrics of the reference trellis (pm[j] == pm[j+S/2]) live in that lane's
+//   registers (L<=5) or in a private shared-memory column (L>=6), so a stage is S adds and
+//   S/2 mins with no cross-lane traffic.  The 32 lanes of a warp move data between HBM and
+//   their frames through 32x32 fp32 tiles staged in shared memory, so every global access is a
+//   full 128-byte line even though each lane walks its own row.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/mvn_b200.h"
+
+namespace mvn {
+
+constexpr int kH1 = MVN_HIDDEN1;
+constexpr int kH2 = MVN_HIDDEN2;
+// fp32(ln sqrt(2 pi)); va_detector.py:68 subtracts the double constant as an fp32 scalar.
+constexpr float kLogSqrt2Pi = 0.9189385175704956f;
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---------------------------------------------------------------- host-side error plumbing
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+void note_launch();
+#define MVN_CUDA(call)                                               \
+    do {                                                             \
+        cudaError_t e__ = (call);                                    \
+        if (e__ != cudaSuccess) return ::mvn::cuda_fail(e__, #call); \
+    } while (0)
+
+int sm_count();
+
+// ---------------------------------------------------------------- tiles
+// A warp-private tile holds 32 rows x 32 fp32; rows padded to 36 floats: 16-byte aligned rows,
+// and both the row-wise 128-bit fills and the "lane reads its own row" accesses are
+// bank-conflict free ((36*lane + c) mod 32 = 4*lane + c).
+constexpr int kTileLd = 36;
+constexpr int kTileFloats = 32 * kTileLd;
+
+__device__ __forceinline__ float4 ldg_stream4(const float *p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ldg_stream1(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+// Rows [row0,row0+32) x columns [c0,c0+32) of a row-major matrix (leading dimension ld floats,
+// `ncols` valid columns, `nrows` valid rows) -> tile.  Out-of-range elements read as 0.
+// vec: ld % 4 == 0, ncols % 4 == 0 and 16-byte aligned base (checked by the host wrapper).
+__device__ __forceinline__ void warp_load_tile(const float *__restrict__ src, int64_t nrows, int64_t ld,
+                                               int64_t ncols, int64_t row0, int64_t c0, float *tile,
+                                               int lane, bool vec) {
+    if (vec) {
+        float4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int r = 4 * i + (lane >> 3);
+            const int c = (lane & 7) * 4;
+            const int64_t row = row0 + r;
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < nrows && c0 + c < ncols) v[i] = ldg_stream4(src + row * ld + c0 + c);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int r = 4 * i + (lane >> 3);
+            const int c = (lane & 7) * 4;
+            *reinterpret_cast<float4 *>(tile + r * kTileLd + c) = v[i];
+        }
+    } else {
+#pragma unroll 8
+        for (int r = 0; r < 32; r++) {
+            const int64_t row = row0 + r;
+            float v = 0.f;
+            if (row < nrows && c0 + lane < ncols) v = ldg_stream1(src + row * ld + c0 + lane);
+            tile[r * kTileLd + lane] = v;
+        }
+    }
+    __syncwarp();
+}
+
+// Each lane holds a 32-step decision mask for row row0+lane; the warp writes them as fp32 0/1
+// into dst[row][c0 .. c0+32) with full-line stores.
+__device__ __forceinline__ void warp_store_bits_f32(float *__restrict__ dst, int64_t nrows, int64_t ld,
+                                                    int64_t ncols, int64_t row0, int64_t c0, uint32_t bits,
+                                                    int lane, bool vec) {
+    if (vec) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int r = 4 * i + (lane >> 3);
+            const int c = (lane & 7) * 4;
+            const uint32_t m = __shfl_sync(kFull, bits, r) >> c;
+            const int64_t row = row0 + r;
+            if (row < nrows && c0 + c < ncols) {
+                float4 v = make_float4(float(m & 1u), float((m >> 1) & 1u), float((m >> 2) & 1u),
+                                       float((m >> 3) & 1u));
+                *reinterpret_cast<float4 *>(dst + row * ld + c0 + c) = v;
+            }
+        }
+    } else {
+#pragma unroll 8
+        for (int r = 0; r < 32; r++) {
+            const uint32_t m = __shfl_sync(kFull, bits, r);
+            const int64_t row = row0 + r;
+            if (row < nrows && c0 + lane < ncols) dst[row * ld + c0 + lane] = float((m >> lane) & 1u);
+        }
+    }
+}
+
+__device__ __forceinline__ bool is_vec_ok(const void *p, int64_t ld, int64_t ncols) {
+    return ((reinterpret_cast<uintptr_t>(p) & 15u) == 0) && (ld % 4 == 0) && (ncols % 4 == 0);
+}
+
+// ---------------------------------------------------------------- trellis engines
+// Both engines implement Appendix A of SURVEY.md exactly:
+//   decide(): (lowest s attaining min_s pm[s]) & 1  — the argmin always lies in [0,S/2)
+//   step   : tmp[s] = pm[s mod H] + cost[s];  pm'[j] = min(tmp[2j], tmp[2j+1]), j < H = S/2
+// fminf == torch.min for the non-NaN values that occur; ties keep the lower index because the
+// scan only replaces on a strict '<'.
+template <int L>
+struct TrellisDims {
+    static constexpr int S = 1 << L;
+    static constexpr int H = (S >= 2) ? S / 2 : 1;
+    static constexpr int C = (S < 16) ? S : 16;  // source states consumed per chunk
+    static constexpr int NCH = S / C;
+};
+
+// Register-resident path metrics (L <= 5: at most 16 distinct metrics per frame).
+template <int L>
+struct RegTrellis {
+    static constexpr int S = TrellisDims<L>::S, H = TrellisDims<L>::H, C = TrellisDims<L>::C;
+    float pm[H];
+    float nw[H];
+    __device__ __forceinline__ void reset() {
+#pragma unroll
+        for (int h = 0; h < H; h++) pm[h] = 0.f;
+    }
+    __device__ __forceinline__ uint32_t decide() const {
+        float best = pm[0];
+        uint32_t bit = 0;
+#pragma unroll
+        for (int h = 1; h < H; h++) {
+            const bool lt = pm[h] < best;
+            best = fminf(best, pm[h]);
+            bit = lt ? uint32_t(h & 1) : bit;
+        }
+        return bit;
+    }
+    // Chunk c covers source states [c*C, c*C+C) and produces new states [c*C/2, c*C/2 + C/2).
+    // cost[i] is the branch cost of source state c*C+i.  Returns the C/2 survivor bits.
+    template <int c>
+    __device__ __forceinline__ uint32_t step_chunk(const float (&cost)[C]) {
+        uint32_t surv = 0;
+#pragma unroll
+        for (int i = 0; i < C / 2; i++) {
+            const float a = pm[(c * C + 2 * i) % H] + cost[2 * i];
+            const float b = pm[(c * C + 2 * i + 1) % H] + cost[2 * i + 1];
+            nw[c * (C / 2) + i] = fminf(a, b);
+            surv |= uint32_t(b < a) << i;
+        }
+        return surv;
+    }
+    __device__ __forceinline__ void commit() {
+#pragma unroll
+        for (int h = 0; h < H; h++) pm[h] = nw[h];
+    }
+    __device__ __forceinline__ float metric(int h) const { return pm[h]; }
+};
+
+// Shared-memory path metrics (L >= 6): column `col` of a [2][H][ncols] fp32 array, one column
+// per frame, consecutive threads -> consecutive columns (conflict-free).
+template <int L>
+struct SmemTrellis {
+    static constexpr int S = TrellisDims<L>::S, H = TrellisDims<L>::H, C = TrellisDims<L>::C;
+    float *base;  // &array[0][0][col]
+    int ncols;
+    int cur;
+    __device__ __forceinline__ void init(float *array, int ncols_, int col) {
+        base = array + col;
+        ncols = ncols_;
+        cur = 0;
+    }
+    static __host__ __device__ constexpr size_t bytes(int ncols_) { return size_t(2) * H * ncols_ * sizeof(float); }
+    __device__ __forceinline__ float &at(int buf, int h) const { return base[(size_t(buf) * H + h) * ncols]; }
+    __device__ __forceinline__ void reset() {
+        for (int h = 0; h < H; h++) at(0, h) = 0.f;
+        cur = 0;
+    }
+    __device__ __forceinline__ uint32_t decide() const {
+        float best = at(cur, 0);
+        uint32_t bit = 0;
+#pragma unroll 8
+        for (int h = 1; h < H; h++) {
+            const float v = at(cur, h);
+            const bool lt = v < best;
+            best = fminf(best, v);
+            bit = lt ? uint32_t(h & 1) : bit;
+        }
+        return bit;
+    }
+    __device__ __forceinline__ uint32_t step_chunk_rt(int c, const float (&cost)[C]) {
+        uint32_t surv = 0;
+#pragma unroll
+        for (int i = 0; i < C / 2; i++) {
+            const float a = at(cur, (c * C + 2 * i) % H) + cost[2 * i];
+            const float b = at(cur, (c * C + 2 * i + 1) % H) + cost[2 * i + 1];
+            at(cur ^ 1, c * (C / 2) + i) = fminf(a, b);
+            surv |= uint32_t(b < a) << i;
+        }
+        return surv;
+    }
+    __device__ __forceinline__ void commit() { cur ^= 1; }
+    __device__ __forceinline__ float metric(int h) const { return at(cur, h); }
+};
+
+// ---------------------------------------------------------------- fused BER/FER accounting
+struct ErrAcc {
+    unsigned bit_errs = 0, frame_errs = 0, bits = 0, frames = 0;
+    __device__ __forceinline__ void flush(unsigned long long *counters) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            bit_errs += __shfl_xor_sync(kFull, bit_errs, o);
+            frame_errs += __shfl_xor_sync(kFull, frame_errs, o);
+            bits += __shfl_xor_sync(kFull, bits, o);
+            frames += __shfl_xor_sync(kFull, frames, o);
+        }
+        if ((threadIdx.x & 31) == 0 && frames) {
+            atomicAdd(counters + MVN_CNT_BIT_ERRORS, (unsigned long long)bit_errs);
+            atomicAdd(counters + MVN_CNT_FRAME_ERRORS, (unsigned long long)frame_errs);
+            atomicAdd(counters + MVN_CNT_BITS, (unsigned long long)bits);
+            atomicAdd(counters + MVN_CNT_FRAMES, (unsigned long long)frames);
+        }
+        bit_errs = frame_errs = bits = frames = 0;
+    }
+};
+
+// Count mismatches between this lane's 32 decided bits and its row of a staged target tile.
+// target.long() truncates toward zero (metrics.py:11-12).
+__device__ __forceinline__ unsigned tile_bit_errors(const float *tile_row, uint32_t bits, int valid_cols) {
+    unsigned e = 0;
+#pragma unroll 8
+    for (int c = 0; c < 32; c++) {
+        const int tgt = int(tile_row[c]);
+        const int bit = int((bits >> c) & 1u);
+        e += (c < valid_cols && tgt != bit) ? 1u : 0u;
+    }
+    return e;
+}
+
+}  // namespace mvn

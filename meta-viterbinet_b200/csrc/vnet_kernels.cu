@@ -1,0 +1,505 @@
+// a6 / a7 + a3 — ViterbiNet priors MLP (1 -> 100 sigmoid -> 50 relu -> S) and the fused
+// priors + ACS + decision kernel.  Reference semantics: detectors/VNET/vnet_detector.py:27-61,
+// detectors/META_VNET/meta_vnet_detector.py:24-45.
+//
+// FP32-pipe bound (11 832 flop and 8 HBM bytes per symbol at S=16), so the design goal is to
+// keep the FMA pipe busy:
+//   * one lane owns M frames; per stage it evaluates the MLP for its M samples entirely in
+//     registers (100 layer-2 accumulators for M=2) and then runs the ACS on its private metrics;
+//   * weights live in shared memory, transposed so that one warp-uniform (broadcast) 128-bit load
+//     feeds two packed fma.rn.f32x2 (SASS FFMA2) per frame: the packed form needs one issue slot
+//     per two FMAs, which leaves slots for the LDS/MUFU/ALU work of the same warp;
+//   * sigmoid(a) = 1/(1+2^(-a log2 e)) with -log2 e folded into W1/b1 when the weights are staged:
+//     one FFMA + MUFU.EX2 + FADD + MUFU.RCP per hidden unit.
+#include <algorithm>
+#include <type_traits>
+
+#include "mvn_common.cuh"
+
+namespace mvn {
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 pack2(float a, float b) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float &a, float &b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+// d = a*b + c on both halves, round-to-nearest-even (same rounding as two scalar fmaf).
+// Accumulating form (c += a*b) with a read-write operand so that ptxas keeps the accumulator in place.
+__device__ __forceinline__ void ffma2_acc(u64 &c, u64 a, u64 b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// Shared-memory weight loads as volatile asm: the weights are loop-invariant across stages, and
+// without this NVVM hoists them out of the stage loop into (spilled) registers.
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void lds128(uint32_t addr, u64 &a, u64 &b) {
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
+__device__ __forceinline__ u64 lds64(uint32_t addr) {
+    u64 a;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(a) : "r"(addr));
+    return a;
+}
+__device__ __forceinline__ float2 lds64f(uint32_t addr) {
+    float2 a;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a.x), "=f"(a.y) : "r"(addr));
+    return a;
+}
+
+// ------------------------------------------------------------------ staged weights
+#ifndef MVN_K_UNROLL
+#define MVN_K_UNROLL 5
+#endif
+constexpr int kKUnroll = MVN_K_UNROLL;
+constexpr int kW2Ld = 52;  // 50 outputs padded to 13 x 128-bit
+template <int L>
+struct VnetSmem {
+    static constexpr int S = 1 << L;
+    static constexpr int S4 = (S + 3) / 4 * 4;
+    static constexpr int oW1B1 = 0;                     // [101][2]: (-log2e*w1, -log2e*b1), one pad pair
+    static constexpr int oB2 = 204;                     // [52]
+    static constexpr int oW2T = oB2 + kW2Ld;            // [100][52]   W2T[k][o] = w2[o][k]
+    static constexpr int oB3 = oW2T + kH1 * kW2Ld;      // [S4]
+    static constexpr int oW3T = oB3 + S4;               // [50][S]     W3T[j][s] = w3[s][j]
+    static constexpr int kFloats = (oW3T + kH2 * S + 3) / 4 * 4;
+};
+
+struct VnetWeights {
+    const float *w1, *b1, *w2, *b2, *w3, *b3;
+};
+
+template <int L>
+__device__ void stage_weights(float *sm, const VnetWeights &w, int tid, int nt) {
+    using W = VnetSmem<L>;
+    constexpr int S = W::S;
+    const float kNegLog2e = -1.4426950408889634f;
+    for (int i = tid; i < 102; i += nt) {
+        sm[W::oW1B1 + 2 * i] = i < kH1 ? w.w1[i] * kNegLog2e : 0.f;
+        sm[W::oW1B1 + 2 * i + 1] = i < kH1 ? w.b1[i] * kNegLog2e : 0.f;
+    }
+    for (int i = tid; i < kW2Ld; i += nt) sm[W::oB2 + i] = i < kH2 ? w.b2[i] : 0.f;
+    for (int i = tid; i < kH2 * kH1; i += nt) {
+        const int o = i / kH1, k = i % kH1;
+        sm[W::oW2T + k * kW2Ld + o] = w.w2[i];
+    }
+    for (int i = tid; i < kH1 * 2; i += nt) sm[W::oW2T + (i >> 1) * kW2Ld + kH2 + (i & 1)] = 0.f;
+    for (int i = tid; i < W::S4; i += nt) sm[W::oB3 + i] = i < S ? w.b3[i] : 0.f;
+    for (int i = tid; i < S * kH2; i += nt) {
+        const int s = i / kH2, j = i % kH2;
+        sm[W::oW3T + j * S + s] = w.w3[i];
+    }
+}
+
+// ------------------------------------------------------------------ the MLP, M samples per lane
+template <int M>
+__device__ __forceinline__ void sigmoid_unit(uint32_t w1b1, int k, const float (&y)[M], float (&h)[M]) {
+    const float2 wb = lds64f(w1b1 + 8 * k);
+#pragma unroll
+    for (int m = 0; m < M; m++) h[m] = rcp_approx(1.f + ex2_approx(fmaf(y[m], wb.x, wb.y)));
+}
+
+// layers 1+2 (+ReLU): y[M] -> h2[M][50]
+template <int L, int M>
+__device__ __forceinline__ void mlp_hidden(const float *sm, const float (&y)[M], float (&h2)[M][kH2]) {
+    using W = VnetSmem<L>;
+    const uint32_t sa = smem_addr(sm);
+    u64 acc[M][25];
+#pragma unroll
+    for (int i = 0; i < 25; i++) {
+        const u64 b = lds64(sa + 4 * W::oB2 + 8 * i);
+#pragma unroll
+        for (int m = 0; m < M; m++) acc[m][i] = b;
+    }
+    float hc[M], hn[M];
+    sigmoid_unit<M>(sa + 4 * W::oW1B1, 0, y, hc);
+#pragma unroll kKUnroll
+    for (int k = 0; k < kH1; k++) {
+        sigmoid_unit<M>(sa + 4 * W::oW1B1, k + 1, y, hn);  // entry 100 is a zero pad
+        const uint32_t wr = sa + 4 * (W::oW2T + k * kW2Ld);
+        u64 hh[M];
+#pragma unroll
+        for (int m = 0; m < M; m++) hh[m] = pack2(hc[m], hc[m]);
+#pragma unroll
+        for (int q = 0; q < 12; q++) {
+            u64 wx, wy;
+            lds128(wr + 16 * q, wx, wy);
+#pragma unroll
+            for (int m = 0; m < M; m++) {
+                ffma2_acc(acc[m][2 * q], hh[m], wx);
+                ffma2_acc(acc[m][2 * q + 1], hh[m], wy);
+            }
+        }
+        const u64 wl = lds64(wr + 16 * 12);
+#pragma unroll
+        for (int m = 0; m < M; m++) ffma2_acc(acc[m][24], hh[m], wl);
+#pragma unroll
+        for (int m = 0; m < M; m++) hc[m] = hn[m];
+    }
+#pragma unroll
+    for (int m = 0; m < M; m++)
+#pragma unroll
+        for (int i = 0; i < 25; i++) {
+            float a, b;
+            unpack2(acc[m][i], a, b);
+            h2[m][2 * i] = fmaxf(a, 0.f);
+            h2[m][2 * i + 1] = fmaxf(b, 0.f);
+        }
+}
+
+// layer 3 for output states [c*C, c*C + C): p[m][i] = b3 + sum_j h2[m][j] W3T[j][c*C+i]
+template <int L, int M>
+__device__ __forceinline__ void mlp_out_chunk(const float *sm, int c, const float (&h2)[M][kH2],
+                                              float (&p)[M][TrellisDims<L>::C]) {
+    using W = VnetSmem<L>;
+    constexpr int S = W::S, C = TrellisDims<L>::C, P = C / 2;
+    const uint32_t sa = smem_addr(sm);
+    u64 acc[M][P];
+#pragma unroll
+    for (int i = 0; i < P; i++) {
+        const u64 b = lds64(sa + 4 * (W::oB3 + c * C) + 8 * i);
+#pragma unroll
+        for (int m = 0; m < M; m++) acc[m][i] = b;
+    }
+    const uint32_t w3 = sa + 4 * (W::oW3T + c * C);
+#pragma unroll
+    for (int j = 0; j < kH2; j++) {
+        u64 w[P];
+        if constexpr (C >= 4) {
+#pragma unroll
+            for (int i = 0; i < C / 4; i++) lds128(w3 + 4 * (j * S + 4 * i), w[2 * i], w[2 * i + 1]);
+        } else {
+            w[0] = lds64(w3 + 4 * (j * S));
+        }
+#pragma unroll
+        for (int m = 0; m < M; m++) {
+            const u64 hh = pack2(h2[m][j], h2[m][j]);
+#pragma unroll
+            for (int i = 0; i < P; i++) ffma2_acc(acc[m][i], hh, w[i]);
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < M; m++)
+#pragma unroll
+        for (int i = 0; i < P; i++) unpack2(acc[m][i], p[m][2 * i], p[m][2 * i + 1]);
+}
+
+// =====================================================================================
+// a6: priors only, symbol-parallel ('train' phase forward, parity export, small batches)
+// =====================================================================================
+template <int L, int NT>
+__global__ void __launch_bounds__(NT) vnet_priors_kernel(const float *__restrict__ y, int64_t N, VnetWeights w,
+                                                          float *__restrict__ priors) {
+    using D = TrellisDims<L>;
+    constexpr int S = D::S, C = D::C, NCH = D::NCH, M = 2;
+    extern __shared__ __align__(16) float smem[];
+    stage_weights<L>(smem, w, threadIdx.x, NT);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t n_warps = (int64_t(gridDim.x) * NT) >> 5;
+    for (int64_t base = ((int64_t(blockIdx.x) * NT + threadIdx.x) >> 5) * 64; base < N; base += n_warps * 64) {
+        int64_t n[M];
+        float yv[M];
+#pragma unroll
+        for (int m = 0; m < M; m++) {
+            n[m] = base + 32 * m + lane;
+            yv[m] = n[m] < N ? y[n[m]] : 0.f;
+        }
+        float h2[M][kH2];
+        mlp_hidden<L, M>(smem, yv, h2);
+        for (int c = 0; c < NCH; c++) {
+            float p[M][C];
+            mlp_out_chunk<L, M>(smem, c, h2, p);
+#pragma unroll
+            for (int m = 0; m < M; m++) {
+                if (n[m] < N) {
+                    float *dst = priors + n[m] * S + c * C;
+                    if constexpr (C >= 4) {
+#pragma unroll
+                        for (int i = 0; i < C; i += 4)
+                            *reinterpret_cast<float4 *>(dst + i) = make_float4(p[m][i], p[m][i + 1], p[m][i + 2], p[m][i + 3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < C; i++) dst[i] = p[m][i];
+                    }
+                }
+            }
+        }
+    }
+}
+
+// =====================================================================================
+// a6+a3 fused
+// =====================================================================================
+struct VnetParams {
+    const float *y;
+    int64_t B;
+    int T, n_stages;
+    VnetWeights w;
+    int out_format;
+    void *decoded;
+    float *priors_out;
+    const float *target;
+    int target_T, pilot_period;
+    unsigned long long *counters;
+    int64_t n_warp_tiles;  // tiles of 32*M frames
+};
+
+template <int L>
+struct FusedCfg {
+    static constexpr bool kRegPm = (L <= 4);
+    static constexpr int M = (L <= 7) ? 2 : 1;
+    static constexpr int NT = (L <= 5) ? 256 : 128;
+};
+
+template <int L>
+__global__ void __launch_bounds__(FusedCfg<L>::NT, 1) vnet_decode_kernel(VnetParams p) {
+    using D = TrellisDims<L>;
+    using Cfg = FusedCfg<L>;
+    using W = VnetSmem<L>;
+    constexpr int S = D::S, C = D::C, NCH = D::NCH, M = Cfg::M, NT = Cfg::NT;
+    constexpr int WARPS = NT / 32;
+    using Tr = typename std::conditional<Cfg::kRegPm, RegTrellis<L>, SmemTrellis<L>>::type;
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *tiles = smem + W::kFloats + warp * (M * kTileFloats);
+
+    stage_weights<L>(smem, p.w, threadIdx.x, NT);
+    __syncthreads();
+
+    Tr tr[M];
+    if constexpr (!Cfg::kRegPm) {
+#pragma unroll
+        for (int m = 0; m < M; m++) tr[m].init(smem + W::kFloats + WARPS * M * kTileFloats, NT * M, m * NT + threadIdx.x);
+    }
+
+    const bool vec_in = is_vec_ok(p.y, p.T, p.T);
+    const bool vec_out = p.out_format == MVN_OUT_F32 && is_vec_ok(p.decoded, p.T, p.T);
+    const bool vec_tgt = p.target && is_vec_ok(p.target, p.target_T, p.target_T);
+    const int n_words = (p.T + 31) / 32;
+    ErrAcc acc;
+
+    for (int64_t wt = int64_t(blockIdx.x) * WARPS + warp; wt < p.n_warp_tiles; wt += int64_t(gridDim.x) * WARPS) {
+        const int64_t row0 = wt * (32 * M);
+        unsigned frame_bit_errs[M];
+#pragma unroll
+        for (int m = 0; m < M; m++) {
+            tr[m].reset();
+            frame_bit_errs[m] = 0;
+        }
+        for (int t0 = 0; t0 < p.T; t0 += 32) {
+            uint32_t bits[M];
+#pragma unroll
+            for (int m = 0; m < M; m++) bits[m] = 0;
+            const int t_end = min(32, p.n_stages - t0);
+            if (t_end > 0) {
+#pragma unroll
+                for (int m = 0; m < M; m++)
+                    warp_load_tile(p.y, p.B, p.T, p.T, row0 + 32 * m, t0, tiles + m * kTileFloats, lane, vec_in);
+                for (int tt = 0; tt < t_end; tt++) {
+                    float yv[M];
+#pragma unroll
+                    for (int m = 0; m < M; m++) yv[m] = tiles[m * kTileFloats + lane * kTileLd + tt];
+                    float h2[M][kH2];
+                    mlp_hidden<L, M>(smem, yv, h2);
+#pragma unroll
+                    for (int m = 0; m < M; m++) bits[m] |= tr[m].decide() << tt;
+                    if constexpr (Cfg::kRegPm) {
+                        static_assert(!Cfg::kRegPm || NCH == 1, "register trellis in the fused kernel: S <= 16");
+                        float pr[M][C];
+                        mlp_out_chunk<L, M>(smem, 0, h2, pr);
+#pragma unroll
+                        for (int m = 0; m < M; m++) {
+                            float cost[C];
+#pragma unroll
+                            for (int i = 0; i < C; i++) cost[i] = -pr[m][i];  // vnet_detector.py:57
+                            tr[m].template step_chunk<0>(cost);
+                            tr[m].commit();
+                            const int64_t b = row0 + 32 * m + lane;
+                            if (p.priors_out && b < p.B) {
+                                float *dst = p.priors_out + (b * p.T + t0 + tt) * S;
+#pragma unroll
+                                for (int i = 0; i < C; i++) dst[i] = pr[m][i];
+                            }
+                        }
+                    } else {
+                        for (int c = 0; c < NCH; c++) {
+                            float pr[M][C];
+                            mlp_out_chunk<L, M>(smem, c, h2, pr);
+#pragma unroll
+                            for (int m = 0; m < M; m++) {
+                                float cost[C];
+#pragma unroll
+                                for (int i = 0; i < C; i++) cost[i] = -pr[m][i];
+                                tr[m].step_chunk_rt(c, cost);
+                                const int64_t b = row0 + 32 * m + lane;
+                                if (p.priors_out && b < p.B) {
+                                    float *dst = p.priors_out + (b * p.T + t0 + tt) * S + c * C;
+#pragma unroll
+                                    for (int i = 0; i < C; i++) dst[i] = pr[m][i];
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int m = 0; m < M; m++) tr[m].commit();
+                    }
+                }
+                __syncwarp();
+            }
+#pragma unroll
+            for (int m = 0; m < M; m++) {
+                const int64_t b = row0 + 32 * m + lane;
+                if (p.decoded) {
+                    if (p.out_format == MVN_OUT_F32)
+                        warp_store_bits_f32(static_cast<float *>(p.decoded), p.B, p.T, p.T, row0 + 32 * m, t0, bits[m],
+                                            lane, vec_out);
+                    else if (b < p.B)
+                        static_cast<uint32_t *>(p.decoded)[b * n_words + t0 / 32] = bits[m];
+                }
+                if (p.target && t0 < p.target_T) {
+                    float *tt_tile = tiles + m * kTileFloats;  // the y tile of this block is consumed
+                    warp_load_tile(p.target, p.B, p.target_T, p.target_T, row0 + 32 * m, t0, tt_tile, lane, vec_tgt);
+                    frame_bit_errs[m] += tile_bit_errors(tt_tile + lane * kTileLd, bits[m], p.target_T - t0);
+                    __syncwarp();
+                }
+            }
+        }
+        if (p.target) {
+#pragma unroll
+            for (int m = 0; m < M; m++) {
+                const int64_t b = row0 + 32 * m + lane;
+                const bool counted = b < p.B && !(p.pilot_period > 0 && b % p.pilot_period == 0);
+                if (counted) {
+                    acc.bit_errs += frame_bit_errs[m];
+                    acc.frame_errs += frame_bit_errs[m] ? 1u : 0u;
+                    acc.bits += unsigned(p.target_T);
+                    acc.frames += 1u;
+                }
+            }
+            acc.flush(p.counters);
+        }
+    }
+}
+
+template <int L>
+static size_t fused_smem_bytes() {
+    using Cfg = FusedCfg<L>;
+    size_t fl = VnetSmem<L>::kFloats + size_t(Cfg::NT / 32) * Cfg::M * kTileFloats;
+    size_t bytes = fl * sizeof(float);
+    if (!Cfg::kRegPm) bytes += SmemTrellis<L>::bytes(Cfg::NT * Cfg::M);
+    return bytes;
+}
+
+template <int L>
+static int launch_fused(const VnetParams &p, cudaStream_t st) {
+    using Cfg = FusedCfg<L>;
+    const size_t smem = fused_smem_bytes<L>();
+    auto kern = vnet_decode_kernel<L>;
+    MVN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    const int warps = Cfg::NT / 32;
+    const int64_t need = (p.n_warp_tiles + warps - 1) / warps;
+    const int grid = int(std::min<int64_t>(need, sm_count()));
+    kern<<<grid, Cfg::NT, smem, st>>>(p);
+    note_launch();
+    MVN_CUDA(cudaGetLastError());
+    return MVN_OK;
+}
+
+template <int L>
+static int launch_priors(const float *y, int64_t N, const VnetWeights &w, float *priors, cudaStream_t st) {
+    constexpr int NT = 128;
+    const size_t smem = VnetSmem<L>::kFloats * sizeof(float);
+    auto kern = vnet_priors_kernel<L, NT>;
+    MVN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    int per_sm = 1;
+    MVN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t need = (N + (NT / 32) * 64 - 1) / ((NT / 32) * 64);
+    const int grid = int(std::min<int64_t>(need, int64_t(sm_count()) * per_sm));
+    kern<<<grid, NT, smem, st>>>(y, N, w, priors);
+    note_launch();
+    MVN_CUDA(cudaGetLastError());
+    return MVN_OK;
+}
+
+#define MVN_DISPATCH_L(L, FN, ...)                               \
+    switch (L) {                                                 \
+        case 1: return FN<1>(__VA_ARGS__);                       \
+        case 2: return FN<2>(__VA_ARGS__);                       \
+        case 3: return FN<3>(__VA_ARGS__);                       \
+        case 4: return FN<4>(__VA_ARGS__);                       \
+        case 5: return FN<5>(__VA_ARGS__);                       \
+        case 6: return FN<6>(__VA_ARGS__);                       \
+        case 7: return FN<7>(__VA_ARGS__);                       \
+        case 8: return FN<8>(__VA_ARGS__);                       \
+        default: set_error("memory_length %d outside [1,8]", L); \
+                 return MVN_ERR_ARG;                             \
+    }
+
+int vnet_decode_impl(const VnetParams &p, int L, cudaStream_t st) { MVN_DISPATCH_L(L, launch_fused, p, st) }
+int vnet_priors_impl(const float *y, int64_t N, int L, const VnetWeights &w, float *priors, cudaStream_t st) {
+    MVN_DISPATCH_L(L, launch_priors, y, N, w, priors, st)
+}
+int vnet_frames_per_warp_tile(int L) { return L <= 7 ? 64 : 32; }
+
+}  // namespace mvn
+
+using namespace mvn;
+
+static bool weights_ok(const float *w1, const float *b1, const float *w2, const float *b2, const float *w3,
+                       const float *b3) {
+    return w1 && b1 && w2 && b2 && w3 && b3;
+}
+
+extern "C" int mvn_vnet_priors(const float *y, int64_t N, int L, const float *w1, const float *b1, const float *w2,
+                               const float *b2, const float *w3, const float *b3, float *priors, void *stream) {
+    if (L < 1 || L > 8) {
+        set_error("memory_length %d outside [1,8]", L);
+        return MVN_ERR_ARG;
+    }
+    if (N < 0 || !weights_ok(w1, b1, w2, b2, w3, b3) || (N > 0 && (!y || !priors))) {
+        set_error("mvn_vnet_priors: bad argument");
+        return MVN_ERR_ARG;
+    }
+    if (N == 0) return MVN_OK;
+    VnetWeights w{w1, b1, w2, b2, w3, b3};
+    return vnet_priors_impl(y, N, L, w, priors, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mvn_vnet_decode(const float *y, int64_t B, int T, int L, int n_stages, const float *w1,
+                               const float *b1, const float *w2, const float *b2, const float *w3, const float *b3,
+                               int out_format, void *decoded, float *priors_out, const float *target, int target_T,
+                               int pilot_period, uint64_t *counters, void *stream) {
+    if (L < 1 || L > 8) {
+        set_error("memory_length %d outside [1,8]", L);
+        return MVN_ERR_ARG;
+    }
+    if (B < 0 || T < 0 || n_stages < 0 || n_stages > T || !weights_ok(w1, b1, w2, b2, w3, b3) ||
+        (B > 0 && T > 0 && !y) || (out_format != MVN_OUT_F32 && out_format != MVN_OUT_BITS)) {
+        set_error("mvn_vnet_decode: bad argument (B=%lld T=%d n_stages=%d)", (long long)B, T, n_stages);
+        return MVN_ERR_ARG;
+    }
+    if (target && (!counters || target_T < 1 || target_T > T)) {
+        set_error("mvn_vnet_decode: target needs counters and 1 <= target_T <= T");
+        return MVN_ERR_ARG;
+    }
+    if (B == 0 || T == 0) return MVN_OK;
+    const int fpt = vnet_frames_per_warp_tile(L);
+    VnetParams p{y, B, T, n_stages, VnetWeights{w1, b1, w2, b2, w3, b3}, out_format, decoded, priors_out, target,
+                 target_T, pilot_period, reinterpret_cast<unsigned long long *>(counters), (B + fpt - 1) / fpt};
+    return vnet_decode_impl(p, L, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,154 @@
+"""Tensor-level wrappers around the C ABI (one function per entry point of include/mvn_b200.h)."""
+import torch
+
+from . import _lib
+from ._lib import OUT_BITS, OUT_F32, check, dev_f32, load, ptr, stream
+
+
+def _mem_len(n_states: int) -> int:
+    L = int(n_states).bit_length() - 1
+    if n_states < 2 or (1 << L) != n_states:
+        raise ValueError(f'n_states must be a power of two >= 2, got {n_states}')
+    return L
+
+
+def _new_out(B, T, out_format, device):
+    if out_format == OUT_F32:
+        return torch.empty((B, T), dtype=torch.float32, device=device)
+    return torch.empty((B, (T + 31) // 32), dtype=torch.int32, device=device)
+
+
+def new_counters(device=None):
+    """[bit errors, frame errors, bits, frames] as int64 (the kernels treat them as uint64)."""
+    return torch.zeros(4, dtype=torch.int64, device=device or _lib.require_cuda())
+
+
+def acs_block(in_prob, llrs, n_states):
+    """One ACS stage (trellis_utils.py:16-30): returns (values [B,S] fp32, indices [B,S] int64)."""
+    L = _mem_len(n_states)
+    in_prob = dev_f32(in_prob)
+    llrs = dev_f32(llrs)
+    B = in_prob.shape[0]
+    if in_prob.dim() != 2 or in_prob.shape[1] != n_states:
+        raise ValueError('in_prob must be [batch, n_states]')
+    if llrs.dim() != 2 or llrs.shape[0] != B or llrs.shape[1] not in (1, n_states):
+        raise ValueError('llrs must be [batch, n_states] or [batch, 1]')
+    out = torch.empty_like(in_prob)
+    idx = torch.empty((B, n_states), dtype=torch.int64, device=in_prob.device)
+    check(load().mvn_acs_block(ptr(in_prob), ptr(llrs), llrs.shape[1], B, L, ptr(out), ptr(idx), stream()))
+    return out, idx
+
+
+def acs_decode(cost, n_stages=None, out_format=OUT_F32, return_final_pm=False, return_survivors=False):
+    """Stage loop on cost [B,T,S] (the a3 loop).  Returns decoded (+ final_pm, + survivors)."""
+    cost = dev_f32(cost)
+    B, T, S = cost.shape
+    L = _mem_len(S)
+    n = T if n_stages is None else int(n_stages)
+    dec = _new_out(B, T, out_format, cost.device)
+    pm = torch.empty((B, S), dtype=torch.float32, device=cost.device) if return_final_pm else None
+    sw = max(1, S // 64)
+    surv = torch.zeros((B, n, sw), dtype=torch.int32, device=cost.device) if return_survivors else None
+    check(load().mvn_acs_decode(ptr(cost), B, T, L, n, out_format, ptr(dec), ptr(pm), ptr(surv), stream()))
+    res = (dec,)
+    if return_final_pm:
+        res += (pm,)
+    if return_survivors:
+        res += (surv,)
+    return res if len(res) > 1 else dec
+
+
+def va_decode(y, state_priors, n_stages=None, out_format=OUT_F32, target=None, pilot_period=0, counters=None,
+              want_decoded=True):
+    """Fused full-CSI Viterbi.  state_priors [n_h, S] fp32 (row per tap block)."""
+    y = dev_f32(y)
+    sp = dev_f32(state_priors)
+    B, T = y.shape
+    n_h, S = sp.shape
+    L = _mem_len(S)
+    n = T if n_stages is None else int(n_stages)
+    dec = _new_out(B, T, out_format, y.device) if want_decoded else None
+    tgt, tT = None, 0
+    if target is not None:
+        tgt = dev_f32(target)
+        tT = tgt.shape[1]
+        if counters is None:
+            raise ValueError('target given without counters')
+    check(load().mvn_va_decode(ptr(y), B, T, L, n, ptr(sp), n_h, out_format, ptr(dec), ptr(tgt), tT, pilot_period,
+                               ptr(counters), stream()))
+    return dec
+
+
+def _weights(weights):
+    ws = [dev_f32(w) for w in weights]
+    if len(ws) != 6:
+        raise ValueError('expected [W1,b1,W2,b2,W3,b3]')
+    S = ws[5].numel()
+    shapes = [(100, 1), (100,), (50, 100), (50,), (S, 50), (S,)]
+    for w, s in zip(ws, shapes):
+        if tuple(w.shape) != s:
+            raise ValueError(f'weight shape {tuple(w.shape)} != {s}')
+    return ws, S
+
+
+def vnet_priors(y, weights):
+    """Priors of the ViterbiNet MLP: y [B,T] -> [B,T,S] (no autograd)."""
+    y = dev_f32(y)
+    ws, S = _weights(weights)
+    L = _mem_len(S)
+    out = torch.empty(tuple(y.shape) + (S,), dtype=torch.float32, device=y.device)
+    check(load().mvn_vnet_priors(ptr(y), y.numel(), L, *[ptr(w) for w in ws], ptr(out), stream()))
+    return out
+
+
+def vnet_decode(y, weights, n_stages=None, out_format=OUT_F32, return_priors=False, target=None, pilot_period=0,
+                counters=None, want_decoded=True):
+    """Fused priors MLP + stage loop + decision."""
+    y = dev_f32(y)
+    ws, S = _weights(weights)
+    L = _mem_len(S)
+    B, T = y.shape
+    n = T if n_stages is None else int(n_stages)
+    dec = _new_out(B, T, out_format, y.device) if want_decoded else None
+    pri = torch.zeros((B, T, S), dtype=torch.float32, device=y.device) if return_priors else None
+    tgt, tT = None, 0
+    if target is not None:
+        tgt = dev_f32(target)
+        tT = tgt.shape[1]
+        if counters is None:
+            raise ValueError('target given without counters')
+    check(load().mvn_vnet_decode(ptr(y), B, T, L, n, *[ptr(w) for w in ws], out_format, ptr(dec), ptr(pri), ptr(tgt),
+                                 tT, pilot_period, ptr(counters), stream()))
+    return (dec, pri) if return_priors else dec
+
+
+def calculate_states(memory_length, transmitted_words):
+    tx = dev_f32(transmitted_words)
+    B, T = tx.shape
+    out = torch.empty(B * T, dtype=torch.int64, device=tx.device)
+    check(load().mvn_calculate_states(ptr(tx), B, T, int(memory_length), ptr(out), stream()))
+    return out
+
+
+def error_counts(prediction, target, pilot_period=0, counters=None, want_rows=True):
+    """Exact integer counts.  Returns (counters int64[4], row_errors uint8 [B] or None)."""
+    p = dev_f32(prediction)
+    t = dev_f32(target)
+    if p.dim() != 2 or t.dim() != 2 or p.shape[0] != t.shape[0]:
+        raise ValueError('prediction/target must be [rows, cols] with equal rows')
+    if p.shape[1] != t.shape[1]:
+        raise RuntimeError(f'The size of tensor a ({p.shape[1]}) must match the size of tensor b ({t.shape[1]})')
+    B, T = p.shape
+    if counters is None:
+        counters = new_counters(p.device)
+    rows = torch.empty(B, dtype=torch.uint8, device=p.device) if want_rows else None
+    check(load().mvn_error_counts(ptr(p), p.stride(0), ptr(t), t.stride(0), B, T, pilot_period, ptr(counters),
+                                  ptr(rows), stream()))
+    return counters, rows
+
+
+def unpack_bits(words, T):
+    """[B, ceil(T/32)] int32 words -> [B,T] fp32 0/1 (host-side convenience for OUT_BITS)."""
+    shifts = torch.arange(32, device=words.device, dtype=torch.int32)
+    bits = (words.unsqueeze(-1) >> shifts) & 1
+    return bits.reshape(words.shape[0], -1)[:, :T].float()

@@ -1,0 +1,398 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on seeded inputs, against
+the golden fixtures produced by the live reference, and — at full size — through size-independent
+properties.  Run on the B200 box: ``python -m pytest tests -m gpu``.
+
+Bars (BASELINE.json north_star / SURVEY.md §8c):
+  * decoded bits, path metrics, survivor indices, labels, error counts: bit-exact;
+  * priors: |kernel - reference| <= 1e-5 * (max |prior| of that symbol's row), fp32;
+  * ViterbiNet decode: (i) the stage loop fed the kernel's own exported priors is bit-exact,
+    (ii) against the full reference forward mismatching bits are counted and each must sit at a
+    near-tie (competing metrics closer than the prior tolerance accumulated over the stages).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import viterbinet_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+PRIOR_RTOL = 1e-5
+
+
+@pytest.fixture(scope='module')
+def mvn():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    import meta_viterbinet_b200 as m
+    return m
+
+
+def cu(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).cuda()
+
+
+def rel_to_rowmax(a, ref):
+    return float(np.max(np.abs(a - ref) / np.max(np.abs(ref), axis=-1, keepdims=True)))
+
+
+def unpack_survivors(words, H):
+    """[B,T,W] int32 -> [B,T,H] {0,1}"""
+    w = words.cpu().numpy().view(np.uint32)
+    bits = (w[..., :, None] >> np.arange(32, dtype=np.uint32)) & 1
+    return bits.reshape(w.shape[0], w.shape[1], -1)[..., :H].astype(np.int8)
+
+
+# ------------------------------------------------------------------------------- a1-a3
+@pytest.mark.parametrize('L', range(3, 9))
+@pytest.mark.parametrize('kind', ['rand', 'tie'])
+def test_acs_decode_golden(mvn, L, kind):
+    g = load_golden('acs')
+    cost = g[f'cost_{kind}_L{L}']
+    dec, pm, surv = mvn.ops.acs_decode(cu(cost), return_final_pm=True, return_survivors=True)
+    assert np.array_equal(dec.cpu().numpy(), g[f'dec_{kind}_L{L}'])
+    assert np.array_equal(pm.cpu().numpy().view(np.uint32), g[f'pm_{kind}_L{L}'].view(np.uint32))
+    H = 2 ** (L - 1)
+    assert np.array_equal(unpack_survivors(surv, H), g[f'surv_{kind}_L{L}'][:, :, :H])
+    assert np.array_equal(g[f'surv_{kind}_L{L}'][:, :, :H], g[f'surv_{kind}_L{L}'][:, :, H:])
+    words = mvn.ops.acs_decode(cu(cost), out_format=mvn.OUT_BITS)
+    assert np.array_equal(mvn.ops.unpack_bits(words, cost.shape[1]).cpu().numpy(), g[f'dec_{kind}_L{L}'])
+
+
+@pytest.mark.parametrize('L', range(1, 9))
+@pytest.mark.parametrize('B,T', [(1, 1), (33, 37), (257, 64), (1000, 45)])
+def test_acs_decode_ragged_vs_oracle(mvn, L, B, T):
+    rng = np.random.RandomState(100 * L + B)
+    S = 2 ** L
+    cost = (rng.randn(B, T, S) * 3).astype(np.float32)
+    cost[::3] = rng.randint(-2, 3, size=cost[::3].shape)        # exact ties in a third of the frames
+    n_stages = max(1, T - 5)
+    ref_dec, ref_pm = orc.acs_decode(cost, n_stages)
+    dec, pm = mvn.ops.acs_decode(cu(cost), n_stages, return_final_pm=True)
+    assert np.array_equal(dec.cpu().numpy(), ref_dec)
+    assert np.array_equal(pm.cpu().numpy(), ref_pm)
+
+
+def test_acs_decode_empty(mvn):
+    out = mvn.ops.acs_decode(torch.zeros(0, 8, 16).cuda())
+    assert out.shape == (0, 8)
+
+
+@pytest.mark.parametrize('L', [1, 3, 4, 8])
+def test_acs_block_matches(mvn, L):
+    rng = np.random.RandomState(L)
+    S = 2 ** L
+    pm = rng.randn(50, S).astype(np.float32)
+    c = rng.randint(-1, 2, size=(50, S)).astype(np.float32)
+    val, idx = mvn.acs_block(cu(pm), cu(c), None, S)
+    rv, ri = orc.acs_stage(pm, c)
+    assert np.array_equal(val.cpu().numpy(), rv) and np.array_equal(idx.cpu().numpy(), ri)
+    assert idx.dtype == torch.int64
+    val1, _ = mvn.acs_block(cu(pm), cu(c[:, :1]), None, S)      # [B,1] broadcast llrs
+    assert np.array_equal(val1.cpu().numpy(), orc.acs_stage(pm, np.broadcast_to(c[:, :1], pm.shape))[0])
+
+
+# ------------------------------------------------------------------------------- a4/a5 VA
+VA_CASES = ['L4_fade1_ecc', 'L4_fade2', 'L4_cost2100_ecc'] + [f'L{L}_static' for L in (3, 5, 6, 7, 8)]
+
+
+@pytest.mark.parametrize('name', VA_CASES)
+def test_va_decode_golden(mvn, name):
+    from meta_viterbinet_b200.channel_taps import state_priors_table
+    g = load_golden('va')
+    L, T = int(g[f'{name}_meta'][0]), int(g[f'{name}_meta'][1])
+    y, h = g[f'{name}_y'], g[f'{name}_h']
+    table = cu(state_priors_table(h, L))
+    dec = mvn.ops.va_decode(cu(y), table, T)
+    assert np.array_equal(dec.cpu().numpy(), g[f'{name}_dec'])
+    W = y.shape[0]
+    for row, i in zip(g[f'{name}_dec_count'], (0, 7, W - 1)):        # eval_by_word shape: B=1, one tap block
+        d1 = mvn.ops.va_decode(cu(y[i:i + 1]), table[i:i + 1].contiguous(), T)
+        assert np.array_equal(d1.cpu().numpy()[0], row)
+    words = mvn.ops.va_decode(cu(y), table, T, out_format=mvn.OUT_BITS)
+    assert np.array_equal(mvn.ops.unpack_bits(words, y.shape[1]).cpu().numpy(), g[f'{name}_dec'])
+
+
+@pytest.mark.parametrize('L', range(1, 9))
+def test_va_decode_random_vs_oracle(mvn, L):
+    rng = np.random.RandomState(L)
+    n_h, reps, T = 7, 19, 50          # B = 133 (ragged), T % 4 != 0 -> scalar staging path
+    h = np.abs(rng.randn(n_h, L)) + 0.1
+    bits = rng.randint(0, 2, size=(n_h * reps, T))
+    y = orc.isi_awgn(bits, np.tile(h, (reps, 1)), 8.0, L, rng).astype(np.float32)
+    ref = orc.va_decode(y, h, L, T - 3)
+    from meta_viterbinet_b200.channel_taps import state_priors_table
+    dec = mvn.ops.va_decode(cu(y), cu(state_priors_table(h, L)), T - 3)
+    assert np.array_equal(dec.cpu().numpy(), ref)
+
+
+def test_va_batch_not_multiple_of_blocks_raises(mvn):
+    with pytest.raises(mvn.MVNError):
+        mvn.ops.va_decode(torch.zeros(10, 8).cuda(), torch.zeros(3, 16).cuda())
+
+
+def test_va_detector_class_matches_reference_run(mvn):
+    """VADetector built like va_trainer.py:32-40 reproduces the reference's decoded words."""
+    g = load_golden('va')
+    for name, kw in [('L4_fade1_ecc', dict(fading=True, fading_taps_type=1)),
+                     ('L4_fade2', dict(fading=True, fading_taps_type=2)),
+                     ('L6_static', dict(fading=False, fading_taps_type=1))]:
+        L, T = int(g[f'{name}_meta'][0]), int(g[f'{name}_meta'][1])
+        y = g[f'{name}_y']
+        det = mvn.VADetector(n_states=2 ** L, memory_length=L, transmission_length=T, val_words=y.shape[0],
+                             channel_type='ISI_AWGN', noisy_est_var=0, channel_coefficients={'train': 'time_decay',
+                                                                                              'val': 'time_decay'}, **kw)
+        out = det(cu(y), 'val', 10.0, 0.2)
+        assert out.dtype == torch.float32 and out.shape == y.shape
+        assert np.array_equal(out.cpu().numpy(), g[f'{name}_dec'])
+        one = det(cu(y[7:8]), 'val', 10.0, 0.2, 7)
+        assert np.array_equal(one.cpu().numpy()[0], g[f'{name}_dec_count'][1])
+        sp = det.compute_state_priors(g[f'{name}_h'])
+        assert np.array_equal(sp.cpu().numpy().view(np.uint32), g[f'{name}_sp'].view(np.uint32))
+        with pytest.raises(NotImplementedError):
+            det(cu(y), 'train', 10.0, 0.2)
+    bad = mvn.VADetector(16, 4, 8, 4, 'OTHER', 0, False, 1, {'train': 'time_decay', 'val': 'time_decay'})
+    with pytest.raises(Exception, match='No such channel defined'):
+        bad(torch.zeros(4, 8).cuda(), 'val', 10.0, 0.2)
+
+
+# ------------------------------------------------------------------------------- a6/a7 priors
+def _w(g, prefix):
+    return [g[f'{prefix}{i}'] for i in range(6)]
+
+
+@pytest.mark.parametrize('tag', ['init', 'trained'])
+def test_vnet_priors_golden(mvn, tag):
+    g = load_golden('vnet')
+    w, y = _w(g, f'{tag}_w'), g['y']
+    pri = mvn.ops.vnet_priors(cu(y), [cu(a) for a in w]).cpu().numpy()
+    assert rel_to_rowmax(pri, g[f'{tag}_priors']) < PRIOR_RTOL
+    exact = orc.vnet_priors(y, w, dtype=np.float64)
+    assert rel_to_rowmax(pri, exact) < PRIOR_RTOL
+
+
+@pytest.mark.parametrize('L', [3, 5, 6, 7, 8])
+def test_vnet_priors_other_sizes(mvn, L):
+    g = load_golden('vnet')
+    w = [g[f'L{L}_w{i}'] for i in range(6)]
+    pri = mvn.ops.vnet_priors(cu(g[f'L{L}_y']), [cu(a) for a in w]).cpu().numpy()
+    assert rel_to_rowmax(pri, g[f'L{L}_priors']) < PRIOR_RTOL
+
+
+@pytest.mark.parametrize('L', [1, 2])
+def test_vnet_priors_tiny_trellis(mvn, L):
+    rng = np.random.RandomState(L)
+    S = 2 ** L
+    w = [rng.randn(100, 1) * .5, rng.randn(100) * .5, rng.randn(50, 100) * .1, rng.randn(50) * .1,
+         rng.randn(S, 50) * .2, rng.randn(S) * .1]
+    w = [a.astype(np.float32) for a in w]
+    y = rng.randn(5, 13).astype(np.float32)
+    pri = mvn.ops.vnet_priors(cu(y), [cu(a) for a in w]).cpu().numpy()
+    assert rel_to_rowmax(pri, orc.vnet_priors(y, w, dtype=np.float64)) < PRIOR_RTOL
+
+
+# ------------------------------------------------------------------------------- a6+a3 fused
+def _explain_mismatches(dec_k, dec_ref, priors_ref, tol_rows):
+    """Every frame whose bits differ from the reference must differ first at a stage where, under
+    the reference's priors, the best and runner-up metrics of different parity are closer than the
+    accumulated prior tolerance."""
+    bad = np.nonzero((dec_k != dec_ref).any(axis=1))[0]
+    for b in bad:
+        t = int(np.nonzero(dec_k[b] != dec_ref[b])[0][0])
+        cost = -priors_ref[b:b + 1].astype(np.float32)
+        _, pm = orc.acs_decode(cost[:, :t], t)          # metrics entering stage t
+        H = pm.shape[1] // 2
+        v = pm[0, :H]
+        even, odd = v[0::2].min(), v[1::2].min()
+        gap = abs(float(even) - float(odd))
+        assert gap <= 2 * t * tol_rows[b], f'frame {b} stage {t}: gap {gap} not a near-tie'
+    return len(bad)
+
+
+@pytest.mark.parametrize('tag', ['init', 'trained'])
+def test_vnet_fused_decode_golden(mvn, tag):
+    g = load_golden('vnet')
+    w, y = _w(g, f'{tag}_w'), g['y']
+    dec, pri = mvn.ops.vnet_decode(cu(y), [cu(a) for a in w], return_priors=True)
+    dec, pri = dec.cpu().numpy(), pri.cpu().numpy()
+    # priors exported by the fused kernel == the priors kernel (same arithmetic), within tolerance of torch
+    pri2 = mvn.ops.vnet_priors(cu(y), [cu(a) for a in w]).cpu().numpy()
+    assert np.array_equal(pri.view(np.uint32), pri2.view(np.uint32))
+    assert rel_to_rowmax(pri, g[f'{tag}_priors']) < PRIOR_RTOL
+    # (i) reference loop on the kernel's own priors: bit-exact
+    ref_own, _ = orc.vnet_decode_from_priors(pri)
+    assert np.array_equal(dec, ref_own)
+    # (ii) against the reference's full forward
+    tol = PRIOR_RTOL * np.abs(g[f'{tag}_priors']).max(axis=(1, 2))
+    n_bad = _explain_mismatches(dec, g[f'{tag}_dec'], g[f'{tag}_priors'], tol)
+    assert n_bad <= 1
+    # small-batch path of the detector (priors kernel + ACS kernel) gives the same bits
+    dec_small = mvn.ops.acs_decode(-cu(pri2))
+    assert np.array_equal(dec_small.cpu().numpy(), dec)
+
+
+def test_vnet_fused_loop_length(mvn):
+    g = load_golden('vnet')
+    w, y = _w(g, 'trained_w'), g['y']
+    dec = mvn.ops.vnet_decode(cu(y), [cu(a) for a in w], n_stages=100).cpu().numpy()
+    assert np.all(dec[:, 100:] == 0)
+    n_bad = (dec != g['trained_dec_T100']).any(axis=1).sum()
+    assert n_bad <= 1
+    with pytest.raises(mvn.MVNError):
+        mvn.ops.vnet_decode(cu(y), [cu(a) for a in w], n_stages=y.shape[1] + 1)
+
+
+@pytest.mark.parametrize('L', range(1, 9))
+@pytest.mark.parametrize('B,T', [(1, 7), (70, 33), (515, 40)])
+def test_vnet_fused_all_trellis_sizes(mvn, L, B, T):
+    rng = np.random.RandomState(10 * L + B)
+    S = 2 ** L
+    w = [rng.randn(100, 1) * .7, rng.randn(100) * .5, rng.randn(50, 100) * .15, rng.randn(50) * .1,
+         rng.randn(S, 50) * .3, rng.randn(S) * .1]
+    w = [a.astype(np.float32) for a in w]
+    y = (rng.randn(B, T) * 1.5).astype(np.float32)
+    dec, pri = mvn.ops.vnet_decode(cu(y), [cu(a) for a in w], n_stages=T - 1, return_priors=True)
+    dec, pri = dec.cpu().numpy(), pri.cpu().numpy()
+    exact = orc.vnet_priors(y, w, dtype=np.float64)
+    assert rel_to_rowmax(pri[:, :T - 1], exact[:, :T - 1]) < PRIOR_RTOL
+    ref_own, _ = orc.vnet_decode_from_priors(pri, T - 1)
+    assert np.array_equal(dec, ref_own)
+    words = mvn.ops.vnet_decode(cu(y), [cu(a) for a in w], n_stages=T - 1, out_format=mvn.OUT_BITS)
+    assert np.array_equal(mvn.ops.unpack_bits(words, T).cpu().numpy(), dec)
+
+
+def test_vnet_detector_classes(mvn):
+    g = load_golden('vnet')
+    w, y = _w(g, 'trained_w'), g['y']
+    det = mvn.VNETDetector(16, {'val': y.shape[1], 'train': y.shape[1]})
+    assert sorted(det.state_dict().keys()) == ['net.0.bias', 'net.0.weight', 'net.2.bias', 'net.2.weight',
+                                               'net.4.bias', 'net.4.weight']
+    with torch.no_grad():
+        for p, a in zip(det.parameters(), w):
+            p.copy_(cu(a))
+    out = det(cu(y), 'val')
+    assert out.shape == y.shape and out.dtype == torch.float32 and out.is_cuda
+    assert (out.cpu().numpy() != g['trained_dec']).any(axis=1).sum() <= 1
+    # batch above the small-batch threshold goes through the fused kernel: same bits
+    reps = 2048 // y.shape[0] + 1
+    big = det(cu(np.tile(y, (reps, 1))), 'val').cpu().numpy()
+    assert np.array_equal(big[:y.shape[0]], out.cpu().numpy())
+    assert np.array_equal(big[-y.shape[0]:], out.cpu().numpy())
+    pri = det(cu(y), 'train')
+    assert pri.shape == y.shape + (16,)
+    assert rel_to_rowmax(pri.detach().cpu().numpy(), g['trained_priors']) < PRIOR_RTOL
+    meta = mvn.META_VNETDetector(16, {'val': y.shape[1], 'train': y.shape[1]})
+    out_m = meta(cu(y), 'val', [cu(a) for a in w])
+    assert np.array_equal(out_m.cpu().numpy(), out.cpu().numpy())
+
+
+# ------------------------------------------------------------------------------- a8 / a12
+@pytest.mark.parametrize('L', [3, 4, 6, 8])
+def test_calculate_states_golden(mvn, L):
+    g = load_golden('labels_metrics')
+    st = mvn.calculate_states(L, cu(g[f'tx_L{L}']))
+    assert st.dtype == torch.int64
+    assert np.array_equal(st.cpu().numpy(), g[f'states_L{L}'])
+
+
+@pytest.mark.parametrize('k', range(4))
+def test_error_rates_golden(mvn, k):
+    g = load_golden('labels_metrics')
+    ber, fer, idx = mvn.calculate_error_rates(cu(g[f'pred_{k}']), cu(g[f'tgt_{k}']))
+    assert ber == g[f'ber_fer_{k}'][0] and fer == g[f'ber_fer_{k}'][1]
+    assert np.array_equal(idx.cpu().numpy(), g[f'idx_{k}'])
+
+
+def test_error_counts_pilots_and_fused_counters(mvn):
+    g = load_golden('vnet')
+    w, y = _w(g, 'trained_w'), g['y']
+    rng = np.random.RandomState(3)
+    tgt = rng.randint(0, 2, size=(y.shape[0], 120)).astype(np.float32)      # target narrower than y (ECC shape)
+    dec = mvn.ops.vnet_decode(cu(y), [cu(a) for a in w])
+    be, fe, nb, nf, _ = orc.error_counts(dec.cpu().numpy()[:, :120], tgt)
+    cnt, rows = mvn.ops.error_counts(dec[:, :120], cu(tgt))
+    assert cnt.tolist() == [be, fe, nb, nf]
+    # pilot rows (index % 25 == 0) excluded, trainer.py:100-102
+    keep = np.array([i for i in range(y.shape[0]) if i % 25 != 0])
+    be, fe, nb, nf, _ = orc.error_counts(dec.cpu().numpy()[keep, :120], tgt[keep])
+    cnt2, _ = mvn.ops.error_counts(dec[:, :120], cu(tgt), pilot_period=25)
+    assert cnt2.tolist() == [be, fe, nb, nf]
+    # fused accumulation inside the decode kernels
+    c3 = mvn.ops.new_counters()
+    mvn.ops.vnet_decode(cu(y), [cu(a) for a in w], target=cu(tgt), pilot_period=25, counters=c3, want_decoded=False)
+    assert c3.tolist() == [be, fe, nb, nf]
+    gv = load_golden('va')
+    from meta_viterbinet_b200.channel_taps import state_priors_table
+    name = 'L4_fade2'
+    yv, hv, bv = gv[f'{name}_y'], gv[f'{name}_h'], gv[f'{name}_b']
+    c4 = mvn.ops.new_counters()
+    dv = mvn.ops.va_decode(cu(yv), cu(state_priors_table(hv, 4)), target=cu(bv), counters=c4)
+    be, fe, nb, nf, _ = orc.error_counts(dv.cpu().numpy(), bv)
+    assert c4.tolist() == [be, fe, nb, nf]
+
+
+# ------------------------------------------------------------------------------- host-buffer pipeline
+def test_host_pipeline_matches_device_path(mvn):
+    import ctypes
+    from meta_viterbinet_b200 import _lib
+    g = load_golden('vnet')
+    w, y = _w(g, 'trained_w'), g['y']
+    yy = np.ascontiguousarray(np.tile(y, (7, 1)))           # 350 frames, chunk 128 -> 3 chunks, ragged tail
+    lib = _lib.load()
+    ctx = ctypes.c_void_p()
+    _lib.check(lib.mvn_ctx_create(ctypes.byref(ctx), torch.cuda.current_device(), 128, yy.shape[1], 4))
+    try:
+        ws = [np.ascontiguousarray(a, dtype=np.float32) for a in w]
+        _lib.check(lib.mvn_ctx_set_vnet_weights_host(ctx, *[a.ctypes.data_as(ctypes.c_void_p) for a in ws]))
+        out = np.empty_like(yy)
+        _lib.check(lib.mvn_ctx_vnet_decode_host(ctx, yy.ctypes.data_as(ctypes.c_void_p), yy.shape[0], yy.shape[1],
+                                                yy.shape[1], 0, out.ctypes.data_as(ctypes.c_void_p)))
+        dev = mvn.ops.vnet_decode(cu(yy), [cu(a) for a in w]).cpu().numpy()
+        assert np.array_equal(out, dev)
+        gv = load_golden('va')
+        from meta_viterbinet_b200.channel_taps import state_priors_table
+        name = 'L4_fade1_ecc'
+        yv = np.ascontiguousarray(gv[f'{name}_y'])
+        tab = state_priors_table(gv[f'{name}_h'], 4)
+        ctx2 = ctypes.c_void_p()
+        _lib.check(lib.mvn_ctx_create(ctypes.byref(ctx2), torch.cuda.current_device(), 50, yv.shape[1], 4))
+        outv = np.empty_like(yv)
+        _lib.check(lib.mvn_ctx_va_decode_host(ctx2, yv.ctypes.data_as(ctypes.c_void_p), yv.shape[0], yv.shape[1],
+                                              yv.shape[1], tab.ctypes.data_as(ctypes.c_void_p), tab.shape[0], 0,
+                                              outv.ctypes.data_as(ctypes.c_void_p)))
+        lib.mvn_ctx_destroy(ctx2)
+        assert np.array_equal(outv, gv[f'{name}_dec'])
+    finally:
+        lib.mvn_ctx_destroy(ctx)
+
+
+# ------------------------------------------------------------------------------- full size
+def test_full_size_properties(mvn):
+    """BASELINE.json sizes (1M frames x 120): frames are independent, so a batch built from 4096
+    distinct frames repeated in shuffled order must decode every copy exactly like the oracle decodes
+    the distinct frame — for the VA (bit-exact) and for the fused ViterbiNet (own-priors protocol)."""
+    from meta_viterbinet_b200.channel_taps import state_priors_table
+    rng = np.random.RandomState(42)
+    L, T, U, B = 4, 120, 4096, 1 << 20
+    h = np.exp(-0.2 * np.arange(L)).reshape(1, L)
+    bits = rng.randint(0, 2, size=(U, T))
+    y_u = orc.isi_awgn(bits, h, 10.0, L, rng).astype(np.float32)
+    perm = torch.randint(0, U, (B,), generator=torch.Generator().manual_seed(1))
+    y = cu(y_u)[perm.cuda()].contiguous()
+    ref = torch.as_tensor(orc.va_decode(y_u, h, L, T)).cuda()
+    cnt = mvn.ops.new_counters()
+    tgt = cu(bits.astype(np.float32))[perm.cuda()].contiguous()
+    dec = mvn.ops.va_decode(y, cu(state_priors_table(h, L)), target=tgt, counters=cnt)
+    assert torch.equal(dec, ref[perm.cuda()])
+    be_u = (ref.cpu().numpy() != bits).sum(axis=1)
+    assert cnt.tolist()[0] == int(be_u[perm.numpy()].sum()) and cnt.tolist()[3] == B
+    g = load_golden('vnet')
+    w = [cu(a) for a in _w(g, 'trained_w')]
+    dec_u, pri_u = mvn.ops.vnet_decode(cu(y_u), w, return_priors=True)
+    own, _ = orc.vnet_decode_from_priors(pri_u.cpu().numpy())
+    assert np.array_equal(dec_u.cpu().numpy(), own)
+    dec_big = mvn.ops.vnet_decode(y, w)
+    assert torch.equal(dec_big, dec_u[perm.cuda()])
+    words = mvn.ops.vnet_decode(y, w, out_format=mvn.OUT_BITS)
+    assert torch.equal(mvn.ops.unpack_bits(words[:5000], T), dec_big[:5000])

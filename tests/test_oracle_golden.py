@@ -152,3 +152,22 @@ def test_hvp_against_finite_differences():
     for h, p, m in zip(hv, gp, gm):
         fd = (p - m) / (2 * eps)
         assert np.max(np.abs(h - fd)) < 1e-6 * max(1.0, np.max(np.abs(fd)))
+
+
+def test_torch_port_matches_oracle():
+    """The CPU-baseline port (what bench.py times) gives the oracle's / reference's bits."""
+    import torch
+    from oracle import torch_port as tp
+    g = load_golden('vnet')
+    w, y = _w(g, 'trained_w'), g['y']
+    net = tp.make_net(16)
+    tp.load_weights(net, w)
+    with torch.no_grad():
+        dec = tp.vnet_forward_val(net, torch.tensor(y), y.shape[1]).numpy()
+    assert np.array_equal(dec, g['trained_dec'])
+    gv = load_golden('va')
+    name = 'L4_fade1_ecc'
+    sp = orc.va_state_priors(gv[f'{name}_h'], 4)
+    with torch.no_grad():
+        dec = tp.va_forward_val(torch.tensor(gv[f'{name}_y']), torch.tensor(sp), int(gv[f'{name}_meta'][1])).numpy()
+    assert np.array_equal(dec, gv[f'{name}_dec'])
