@@ -4,10 +4,12 @@ Import as ``meta_viterbinet_b200`` (the repo-root shim maps the importable name 
 directory, whose name contains a '-').
 """
 from . import _lib, ops
+from . import train
 from ._lib import MVNError, OUT_BITS, OUT_F32
+from .train import BatchedVNetTrainer
 from .detectors import META_VNETDetector, VADetector, VNETDetector
 from .utils.metrics import calculate_error_rates
 from .utils.trellis_utils import acs_block, calculate_states, create_transition_table
 
 __all__ = ['VADetector', 'VNETDetector', 'META_VNETDetector', 'acs_block', 'calculate_states',
-           'create_transition_table', 'calculate_error_rates', 'ops', 'MVNError', 'OUT_F32', 'OUT_BITS']
+           'create_transition_table', 'calculate_error_rates', 'BatchedVNetTrainer', 'train', 'ops', 'MVNError', 'OUT_F32', 'OUT_BITS']

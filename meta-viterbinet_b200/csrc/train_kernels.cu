@@ -1,0 +1,507 @@
+// a9 / a10 / a11 — training of the priors net: CE loss over state labels, hand-derived backward,
+// Hessian-vector product for second-order MAML, torch-compatible Adam.  One CTA per realisation.
+// Reference: trainers/trainer.py:425-453 (meta_train_loop), :492-505 (run_train_loop),
+// trainers/META_VNET/metavnet_trainer.py:41-50 (loss over all symbols), torch.optim.Adam defaults.
+//
+// Every step of the reference depends on the previous one through the weights and the Adam state,
+// so the only parallelism is ACROSS independent runs (SNR points, channel realisations, seeds):
+// R realisations -> R CTAs, each with its own theta / Adam state in HBM and a private scratch slab.
+//
+// Inside a CTA a step is two phases:
+//   phase 1  one thread per symbol: forward, softmax-CE, backward to the pre-activations (and, for
+//            the MAML Hessian-vector product, the forward-over-reverse tangents of all of them);
+//            rows of h1, h2, dz, da2, da1 (and their tangents) go to the scratch slab;
+//   phase 2  one thread per parameter: the sum over symbols of the outer products
+//            (dW2[o][k] = sum_n da2[n][o] h1[n][k], ...), sequential in n => deterministic.
+#include <algorithm>
+
+#include "mvn_common.cuh"
+#include "../../include/mvn_b200_train.h"
+
+namespace mvn {
+
+constexpr int kTrainThreads = 256;
+
+__host__ __device__ constexpr int param_count_s(int S) { return kH1 + kH1 + kH2 * kH1 + kH2 + S * kH2 + S; }
+
+template <int S>
+struct ThetaView {  // offsets into the packed parameter vector (torch parameter order)
+    static constexpr int w1 = 0, b1 = kH1, w2 = 2 * kH1, b2 = w2 + kH2 * kH1, w3 = b2 + kH2, b3 = w3 + S * kH2;
+    static constexpr int P = b3 + S;
+};
+
+// scratch rows per symbol
+template <int S>
+struct Slab {
+    static constexpr int SP = (S + 3) / 4 * 4;
+    static constexpr int oH1 = 0, oH2 = oH1 + kH1, oDZ = oH2 + kH2 + 2, oDA2 = oDZ + SP, oDA1 = oDA2 + kH2 + 2;
+    static constexpr int kHalf = (oDA1 + kH1 + 3) / 4 * 4;  // one set (values); tangents follow
+    static constexpr int kRow = 2 * kHalf;
+    static_assert(oDZ % 4 == 0 && oDA2 % 4 == 0 && oDA1 % 4 == 0, "rows are float4 aligned");
+};
+
+__device__ __forceinline__ float sigmoidf_acc(float a) { return 1.f / (1.f + expf(-a)); }
+
+// ---------------------------------------------------------------------------------------------
+// phase 1.  th: theta in shared memory; tv: tangent direction (TAN only).  If dz_ext != nullptr the
+// upstream gradient w.r.t. the priors is taken from it (autograd backward) instead of the CE loss.
+// ---------------------------------------------------------------------------------------------
+template <int S, bool TAN>
+__device__ __forceinline__ float symbol_pass(const float *__restrict__ th, const float *__restrict__ tv, float y,
+                                             int label, const float *__restrict__ dz_ext, float inv_n,
+                                             float *__restrict__ row) {
+    using TV = ThetaView<S>;
+    using SL = Slab<S>;
+    float *rt = row + SL::kHalf;  // tangent half of the row
+    float h1[kH1];
+    float rh1[TAN ? kH1 : 1];
+#pragma unroll
+    for (int k = 0; k < kH1; k++) {
+        const float h = sigmoidf_acc(fmaf(th[TV::w1 + k], y, th[TV::b1 + k]));
+        h1[k] = h;
+        if (TAN) rh1[k] = h * (1.f - h) * fmaf(tv[TV::w1 + k], y, tv[TV::b1 + k]);
+    }
+#pragma unroll
+    for (int k = 0; k < kH1; k += 4) {
+        *reinterpret_cast<float4 *>(row + SL::oH1 + k) = make_float4(h1[k], h1[k + 1], h1[k + 2], h1[k + 3]);
+        if (TAN) *reinterpret_cast<float4 *>(rt + SL::oH1 + k) = make_float4(rh1[k], rh1[k + 1], rh1[k + 2], rh1[k + 3]);
+    }
+    float z[S], rz[TAN ? S : 1];
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        z[s] = th[TV::b3 + s];
+        if (TAN) rz[s] = tv[TV::b3 + s];
+    }
+#pragma unroll 1
+    for (int o = 0; o < kH2; o++) {
+        const float *w2 = th + TV::w2 + o * kH1;
+        const float *v2 = tv + TV::w2 + o * kH1;
+        float a0 = th[TV::b2 + o], a1 = 0.f, r0 = TAN ? tv[TV::b2 + o] : 0.f, r1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < kH1; k += 2) {
+            a0 = fmaf(w2[k], h1[k], a0);
+            a1 = fmaf(w2[k + 1], h1[k + 1], a1);
+            if (TAN) {
+                r0 = fmaf(v2[k], h1[k], fmaf(w2[k], rh1[k], r0));
+                r1 = fmaf(v2[k + 1], h1[k + 1], fmaf(w2[k + 1], rh1[k + 1], r1));
+            }
+        }
+        const float a2 = a0 + a1;
+        const float h2 = fmaxf(a2, 0.f);
+        const float rh2 = (TAN && a2 > 0.f) ? (r0 + r1) : 0.f;
+        row[SL::oH2 + o] = h2;
+        if (TAN) rt[SL::oH2 + o] = rh2;
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            const float w3 = th[TV::w3 + s * kH2 + o];
+            z[s] = fmaf(w3, h2, z[s]);
+            if (TAN) rz[s] = fmaf(tv[TV::w3 + s * kH2 + o], h2, fmaf(w3, rh2, rz[s]));
+        }
+    }
+    // softmax cross-entropy (torch CrossEntropyLoss, mean reduction -> 1/N folded into dz)
+    float dz[S], rdz[TAN ? S : 1];
+    float loss = 0.f;
+    if (dz_ext) {
+#pragma unroll
+        for (int s = 0; s < S; s++) dz[s] = dz_ext[s];
+    } else {
+        float m = z[0];
+#pragma unroll
+        for (int s = 1; s < S; s++) m = fmaxf(m, z[s]);
+        float sum = 0.f, zl = 0.f;
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            dz[s] = expf(z[s] - m);
+            sum += dz[s];
+            zl = (s == label) ? z[s] : zl;
+        }
+        loss = logf(sum) + m - zl;
+        const float inv = 1.f / sum;
+        float dot = 0.f;
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            dz[s] *= inv;  // p
+            if (TAN) dot = fmaf(dz[s], rz[s], dot);
+        }
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            if (TAN) rdz[s] = dz[s] * (rz[s] - dot) * inv_n;
+            dz[s] = (dz[s] - ((s == label) ? 1.f : 0.f)) * inv_n;
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        row[SL::oDZ + s] = dz[s];
+        if (TAN) rt[SL::oDZ + s] = rdz[s];
+    }
+    // backward to the hidden pre-activations
+    float dh1[kH1], rdh1[TAN ? kH1 : 1];
+#pragma unroll
+    for (int k = 0; k < kH1; k++) {
+        dh1[k] = 0.f;
+        if (TAN) rdh1[k] = 0.f;
+    }
+#pragma unroll 1
+    for (int o = 0; o < kH2; o++) {
+        const bool on = row[SL::oH2 + o] > 0.f;
+        float dh2 = 0.f, rdh2 = 0.f;
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            const float w3 = th[TV::w3 + s * kH2 + o];
+            dh2 = fmaf(w3, dz[s], dh2);
+            if (TAN) rdh2 = fmaf(tv[TV::w3 + s * kH2 + o], dz[s], fmaf(w3, rdz[s], rdh2));
+        }
+        const float da2 = on ? dh2 : 0.f;
+        const float rda2 = (TAN && on) ? rdh2 : 0.f;
+        row[SL::oDA2 + o] = da2;
+        if (TAN) rt[SL::oDA2 + o] = rda2;
+        const float *w2 = th + TV::w2 + o * kH1;
+        const float *v2 = tv + TV::w2 + o * kH1;
+#pragma unroll
+        for (int k = 0; k < kH1; k++) {
+            dh1[k] = fmaf(w2[k], da2, dh1[k]);
+            if (TAN) rdh1[k] = fmaf(v2[k], da2, fmaf(w2[k], rda2, rdh1[k]));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kH1; k++) {
+        const float h = row[SL::oH1 + k];
+        const float s1 = h * (1.f - h);
+        row[SL::oDA1 + k] = dh1[k] * s1;
+        if (TAN) {
+            const float ra1 = fmaf(tv[TV::w1 + k], y, tv[TV::b1 + k]);
+            rt[SL::oDA1 + k] = fmaf(rdh1[k], s1, dh1[k] * s1 * (1.f - 2.f * h) * ra1);
+        }
+    }
+    return loss;
+}
+
+// ---------------------------------------------------------------------------------------------
+// phase 2: out[idx] = sum_n (outer products).  TAN: the tangent (Hessian-vector) combination.
+// ---------------------------------------------------------------------------------------------
+template <int S, bool TAN>
+__device__ __forceinline__ float param_grad(int idx, const float *__restrict__ slab, const float *__restrict__ ys, int n) {
+    using TV = ThetaView<S>;
+    using SL = Slab<S>;
+    constexpr int R = SL::kRow, Hf = SL::kHalf;
+    float acc = 0.f;
+    if (idx < TV::b1) {  // w1[k]
+        const int k = idx;
+        for (int i = 0; i < n; i++) acc = fmaf(slab[i * R + (TAN ? Hf : 0) + SL::oDA1 + k], ys[i], acc);
+    } else if (idx < TV::w2) {  // b1[k]
+        const int k = idx - TV::b1;
+        for (int i = 0; i < n; i++) acc += slab[i * R + (TAN ? Hf : 0) + SL::oDA1 + k];
+    } else if (idx < TV::b2) {  // w2[o][k]
+        const int o = (idx - TV::w2) / kH1, k = (idx - TV::w2) % kH1;
+        for (int i = 0; i < n; i++) {
+            const float *r = slab + i * R;
+            if (TAN)
+                acc = fmaf(r[Hf + SL::oDA2 + o], r[SL::oH1 + k], fmaf(r[SL::oDA2 + o], r[Hf + SL::oH1 + k], acc));
+            else
+                acc = fmaf(r[SL::oDA2 + o], r[SL::oH1 + k], acc);
+        }
+    } else if (idx < TV::w3) {  // b2[o]
+        const int o = idx - TV::b2;
+        for (int i = 0; i < n; i++) acc += slab[i * R + (TAN ? Hf : 0) + SL::oDA2 + o];
+    } else if (idx < TV::b3) {  // w3[s][o]
+        const int s = (idx - TV::w3) / kH2, o = (idx - TV::w3) % kH2;
+        for (int i = 0; i < n; i++) {
+            const float *r = slab + i * R;
+            if (TAN)
+                acc = fmaf(r[Hf + SL::oDZ + s], r[SL::oH2 + o], fmaf(r[SL::oDZ + s], r[Hf + SL::oH2 + o], acc));
+            else
+                acc = fmaf(r[SL::oDZ + s], r[SL::oH2 + o], acc);
+        }
+    } else {  // b3[s]
+        const int s = idx - TV::b3;
+        for (int i = 0; i < n; i++) acc += slab[i * R + (TAN ? Hf : 0) + SL::oDZ + s];
+    }
+    return acc;
+}
+
+// block-wide sum of per-thread losses (deterministic tree)
+__device__ __forceinline__ float block_sum(float v, float *red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+    for (int i = 0; i < kTrainThreads / 32; i++) t += red[i];
+    return t;
+}
+
+// gradient of the mean CE over n symbols at theta `th` -> g (shared or global), returns the loss.
+// Handles n > blockDim by processing symbol blocks of kTrainThreads and accumulating.
+template <int S, bool TAN>
+__device__ float loss_grad(const float *th, const float *tv, const float *__restrict__ y, const int *__restrict__ lab,
+                           int n, float *slab, float *red, float *g_out, bool accumulate_neg_scaled, float scale) {
+    using TV = ThetaView<S>;
+    float loss = 0.f;
+    const float inv_n = 1.f / float(n);
+    for (int base = 0; base < n; base += kTrainThreads) {
+        const int cnt = min(kTrainThreads, n - base);
+        if (int(threadIdx.x) < cnt) {
+            const int i = base + threadIdx.x;
+            loss += symbol_pass<S, TAN>(th, tv, y[i], lab[i], nullptr, inv_n, slab + size_t(threadIdx.x) * Slab<S>::kRow);
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < TV::P; idx += kTrainThreads) {
+            const float v = param_grad<S, TAN>(idx, slab, y + base, cnt);
+            if (accumulate_neg_scaled)
+                g_out[idx] = (base == 0 ? g_out[idx] : g_out[idx]) + scale * v;  // g_out += scale * v
+            else
+                g_out[idx] = (base == 0 ? 0.f : g_out[idx]) + v;
+        }
+        __syncthreads();
+    }
+    return block_sum(loss, red) * inv_n;
+}
+
+struct AdamCfg {
+    float lr, beta1, beta2, eps;
+};
+
+// torch.optim.Adam (single-tensor path): m.lerp_(g, 1-b1); v = b2 v + (1-b2) g^2;
+// denom = sqrt(v)/sqrt(1-b2^t) + eps; theta -= (lr / (1-b1^t)) * m / denom.
+__device__ __forceinline__ void adam_update(float *theta, float *m, float *v, const float *g, int P, int step,
+                                            AdamCfg c) {
+    const float bc1 = float(1.0 - pow(double(c.beta1), double(step)));
+    const float bc2_sqrt = float(sqrt(1.0 - pow(double(c.beta2), double(step))));
+    const float step_size = c.lr / bc1;
+    for (int i = threadIdx.x; i < P; i += kTrainThreads) {
+        const float gi = g[i];
+        const float mi = m[i] + (1.f - c.beta1) * (gi - m[i]);
+        const float vi = c.beta2 * v[i] + (1.f - c.beta2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + c.eps;
+        theta[i] = theta[i] - step_size * (mi / denom);
+    }
+}
+
+struct TrainParams {
+    float *theta, *adam_m, *adam_v;
+    int32_t *adam_step;
+    int R;
+    const float *y_s;
+    const int32_t *lab_s;
+    int Ns;
+    const float *y_q;
+    const int32_t *lab_q;
+    int Nq;
+    float meta_lr;
+    AdamCfg adam;
+    int second_order;
+    float *loss_out, *grad_out;
+    float *workspace;
+    int update;  // 0: only loss/grad
+};
+
+// shared memory: theta | theta' (fast weights) | g (query gradient / tangent) | red[8]
+template <int S, bool META>
+__global__ void __launch_bounds__(kTrainThreads, 1) train_step_kernel(TrainParams p) {
+    using TV = ThetaView<S>;
+    constexpr int P = TV::P;
+    constexpr int PP = (P + 3) / 4 * 4;
+    extern __shared__ __align__(16) float sm[];
+    float *th = sm, *thf = sm + PP, *g = sm + 2 * PP, *red = sm + 3 * PP;
+    float *slab = p.workspace + size_t(blockIdx.x) * kTrainThreads * Slab<S>::kRow;
+    for (int r = blockIdx.x; r < p.R; r += gridDim.x) {
+        float *theta = p.theta + size_t(r) * P;
+        for (int i = threadIdx.x; i < P; i += kTrainThreads) th[i] = theta[i];
+        __syncthreads();
+        float loss;
+        if constexpr (!META) {
+            loss = loss_grad<S, false>(th, th, p.y_s + size_t(r) * p.Ns, p.lab_s + size_t(r) * p.Ns, p.Ns, slab, red, g,
+                                       false, 0.f);
+        } else {
+            const float *ys = p.y_s + size_t(r) * p.Ns, *yq = p.y_q + size_t(r) * p.Nq;
+            const int *ls = p.lab_s + size_t(r) * p.Ns, *lq = p.lab_q + size_t(r) * p.Nq;
+            // inner step on the support set: theta' = theta - meta_lr * grad L_s(theta)   (trainer.py:433-439)
+            loss_grad<S, false>(th, th, ys, ls, p.Ns, slab, red, g, false, 0.f);
+            __syncthreads();
+            for (int i = threadIdx.x; i < P; i += kTrainThreads) thf[i] = th[i] - p.meta_lr * g[i];
+            __syncthreads();
+            // query loss and its gradient at theta'                                   (trainer.py:442-444)
+            loss = loss_grad<S, false>(thf, thf, yq, lq, p.Nq, slab, red, g, false, 0.f);
+            __syncthreads();
+            if (p.second_order) {
+                // d/dtheta L_q(theta - a grad L_s(theta)) = g_q - a H_s(theta) g_q: forward-over-reverse
+                // pass of the support loss at theta along g_q, accumulated into thf (free by now).
+                for (int i = threadIdx.x; i < P; i += kTrainThreads) thf[i] = g[i];
+                __syncthreads();
+                loss_grad<S, true>(th, g, ys, ls, p.Ns, slab, red, thf, true, -p.meta_lr);
+                __syncthreads();
+                for (int i = threadIdx.x; i < P; i += kTrainThreads) g[i] = thf[i];
+            }
+        }
+        __syncthreads();
+        if (p.grad_out)
+            for (int i = threadIdx.x; i < P; i += kTrainThreads) p.grad_out[size_t(r) * P + i] = g[i];
+        if (p.loss_out && threadIdx.x == 0) p.loss_out[r] = loss;
+        if (p.update) {
+            const int step = p.adam_step[r] + 1;
+            adam_update(theta, p.adam_m + size_t(r) * P, p.adam_v + size_t(r) * P, g, P, step, p.adam);
+            __syncthreads();
+            if (threadIdx.x == 0) p.adam_step[r] = step;
+        }
+        __syncthreads();
+    }
+}
+
+// Backward of the priors w.r.t. the six weight tensors for an arbitrary upstream gradient
+// (autograd of the 'train' phase).  Grid over blocks of 256 symbols; partial sums are added to
+// grad_theta with atomics (zeroed by the wrapper).
+template <int S>
+__global__ void __launch_bounds__(kTrainThreads, 1) priors_backward_kernel(const float *__restrict__ y, int64_t N,
+                                                                          const float *__restrict__ theta,
+                                                                          const float *__restrict__ grad_priors,
+                                                                          float *grad_theta, float *workspace) {
+    using TV = ThetaView<S>;
+    constexpr int P = TV::P;
+    extern __shared__ __align__(16) float sm[];
+    float *th = sm;
+    float *ysm = sm + (P + 3) / 4 * 4;
+    float *slab = workspace + size_t(blockIdx.x) * kTrainThreads * Slab<S>::kRow;
+    for (int i = threadIdx.x; i < P; i += kTrainThreads) th[i] = theta[i];
+    __syncthreads();
+    for (int64_t base = int64_t(blockIdx.x) * kTrainThreads; base < N; base += int64_t(gridDim.x) * kTrainThreads) {
+        const int cnt = int(min((long long)kTrainThreads, (long long)(N - base)));
+        if (int(threadIdx.x) < cnt) {
+            const float yv = y[base + threadIdx.x];
+            ysm[threadIdx.x] = yv;
+            symbol_pass<S, false>(th, th, yv, 0, grad_priors + (base + threadIdx.x) * S, 1.f,
+                                  slab + size_t(threadIdx.x) * Slab<S>::kRow);
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < P; idx += kTrainThreads)
+            atomicAdd(grad_theta + idx, param_grad<S, false>(idx, slab, ysm, cnt));
+        __syncthreads();
+    }
+}
+
+static int train_grid(int R) { return std::max(1, std::min(R, 2 * sm_count())); }
+
+template <int S>
+static size_t train_smem() {
+    return (size_t(3) * ((ThetaView<S>::P + 3) / 4 * 4) + 16) * sizeof(float);
+}
+
+template <int L>
+static int launch_train(const TrainParams &p, bool meta, cudaStream_t st) {
+    constexpr int S = 1 << L;
+    const size_t smem = train_smem<S>();
+    const int grid = train_grid(p.R);
+    if (meta) {
+        auto kern = train_step_kernel<S, true>;
+        MVN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        kern<<<grid, kTrainThreads, smem, st>>>(p);
+    } else {
+        auto kern = train_step_kernel<S, false>;
+        MVN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        kern<<<grid, kTrainThreads, smem, st>>>(p);
+    }
+    note_launch();
+    MVN_CUDA(cudaGetLastError());
+    return MVN_OK;
+}
+
+template <int L>
+static int launch_priors_bwd(const float *y, int64_t N, const float *theta, const float *gp, float *gt, float *ws,
+                             cudaStream_t st) {
+    constexpr int S = 1 << L;
+    constexpr int P = ThetaView<S>::P;
+    const size_t smem = (size_t((P + 3) / 4 * 4) + kTrainThreads) * sizeof(float);
+    auto kern = priors_backward_kernel<S>;
+    MVN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    MVN_CUDA(cudaMemsetAsync(gt, 0, P * sizeof(float), st));
+    const int grid = int(std::max<int64_t>(1, std::min<int64_t>((N + kTrainThreads - 1) / kTrainThreads, 2 * sm_count())));
+    kern<<<grid, kTrainThreads, smem, st>>>(y, N, theta, gp, gt, ws);
+    note_launch();
+    MVN_CUDA(cudaGetLastError());
+    return MVN_OK;
+}
+
+static size_t slab_row_floats(int L) {
+    switch (L) {
+        case 1: return Slab<2>::kRow;
+        case 2: return Slab<4>::kRow;
+        case 3: return Slab<8>::kRow;
+        case 4: return Slab<16>::kRow;
+        case 5: return Slab<32>::kRow;
+        default: return 0;
+    }
+}
+
+}  // namespace mvn
+
+using namespace mvn;
+
+#define MVN_TRAIN_DISPATCH(L, FN, ...)                                                          \
+    switch (L) {                                                                                \
+        case 1: return FN<1>(__VA_ARGS__);                                                      \
+        case 2: return FN<2>(__VA_ARGS__);                                                      \
+        case 3: return FN<3>(__VA_ARGS__);                                                      \
+        case 4: return FN<4>(__VA_ARGS__);                                                      \
+        case 5: return FN<5>(__VA_ARGS__);                                                      \
+        default:                                                                                \
+            set_error("training kernels support memory_length 1..5 (reference: 'tested <= 4'), got %d", L); \
+            return MVN_ERR_UNSUPPORTED;                                                         \
+    }
+
+extern "C" int mvn_param_count(int L) { return (L < 1 || L > 8) ? -1 : param_count_s(1 << L); }
+
+extern "C" int64_t mvn_meta_workspace_bytes(int L, int R, int n_max) {
+    (void)n_max;  // symbols are processed in blocks of 256 per CTA, the slab does not grow with n
+    const size_t row = slab_row_floats(L);
+    if (!row || R < 1) return -1;
+    return int64_t(train_grid(R)) * kTrainThreads * row * sizeof(float);
+}
+
+extern "C" int64_t mvn_priors_backward_workspace_bytes(int L, int64_t N) {
+    const size_t row = slab_row_floats(L);
+    if (!row || N < 0) return -1;
+    const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((N + kTrainThreads - 1) / kTrainThreads, 2 * sm_count()));
+    return grid * kTrainThreads * row * sizeof(float);
+}
+
+static int train_common(TrainParams &p, int L, bool meta, void *stream) {
+    if (!p.theta || p.R < 0 || !p.y_s || !p.lab_s || p.Ns < 1 || !p.workspace ||
+        (p.update && (!p.adam_m || !p.adam_v || !p.adam_step)) || (meta && (!p.y_q || !p.lab_q || p.Nq < 1))) {
+        set_error("batched training step: bad argument");
+        return MVN_ERR_ARG;
+    }
+    if (p.R == 0) return MVN_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MVN_TRAIN_DISPATCH(L, launch_train, p, meta, st)
+}
+
+extern "C" int mvn_meta_step_batched(float *theta, float *adam_m, float *adam_v, int32_t *adam_step, int R, int L,
+                                     const float *y_s, const int32_t *lab_s, int Ns, const float *y_q,
+                                     const int32_t *lab_q, int Nq, float meta_lr, float lr, int second_order,
+                                     float *loss_out, float *grad_out, void *workspace, void *stream) {
+    TrainParams p{theta, adam_m, adam_v, adam_step, R, y_s, lab_s, Ns, y_q, lab_q, Nq, meta_lr,
+                  AdamCfg{lr, 0.9f, 0.999f, 1e-8f}, second_order, loss_out, grad_out,
+                  static_cast<float *>(workspace), adam_m != nullptr};
+    return train_common(p, L, true, stream);
+}
+
+extern "C" int mvn_train_step_batched(float *theta, float *adam_m, float *adam_v, int32_t *adam_step, int R, int L,
+                                      const float *y, const int32_t *lab, int N, float lr, float *loss_out,
+                                      float *grad_out, void *workspace, void *stream) {
+    TrainParams p{theta, adam_m, adam_v, adam_step, R, y, lab, N, nullptr, nullptr, 0, 0.f,
+                  AdamCfg{lr, 0.9f, 0.999f, 1e-8f}, 0, loss_out, grad_out, static_cast<float *>(workspace),
+                  adam_m != nullptr};
+    return train_common(p, L, false, stream);
+}
+
+extern "C" int mvn_vnet_priors_backward(const float *y, int64_t N, int L, const float *theta, const float *grad_priors,
+                                        float *grad_theta, void *workspace, void *stream) {
+    if (N < 0 || !theta || !grad_theta || !workspace || (N > 0 && (!y || !grad_priors))) {
+        set_error("mvn_vnet_priors_backward: bad argument");
+        return MVN_ERR_ARG;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MVN_TRAIN_DISPATCH(L, launch_priors_bwd, y, N, theta, grad_priors, grad_theta, static_cast<float *>(workspace), st)
+}

@@ -1,0 +1,137 @@
+"""GPU parity of the batched (meta-)training kernels against (a) the fixtures recorded from the
+reference's own meta_train_loop / run_train_loop and (b) the fp64 oracle on random problems.
+
+Tolerances ("loss and updated theta within 1e-5 relative, fp32, different summation
+order"): loss |d| <= 1e-5 * |loss|; gradients |d| <= 2e-5 * max|g| per tensor; updated parameters
+|d| <= 2e-5 absolute (Adam's first steps move every weight by ~lr = 1e-3, so this is 2 % of one step)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import viterbinet_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def mvn():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    import meta_viterbinet_b200 as m
+    return m
+
+
+def cu(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).cuda()
+
+
+def pack(ws):
+    return np.concatenate([np.asarray(w, dtype=np.float32).reshape(-1) for w in ws])
+
+
+def assert_close_params(theta, ws_ref, atol):
+    ref = pack(ws_ref)
+    assert np.max(np.abs(theta - ref)) < atol, np.max(np.abs(theta - ref))
+
+
+@pytest.mark.parametrize('tag,second', [('maml', True), ('fo', False)])
+def test_meta_step_matches_reference_run(mvn, tag, second):
+    g = load_golden('meta')
+    y, tx = g[f'{tag}_y'], g[f'{tag}_tx']
+    w0 = [g[f'{tag}_w0_{i}'] for i in range(6)]
+    tr = mvn.BatchedVNetTrainer(cu(pack(w0)), 4, lr=1e-3, meta_lr=0.1)
+    for step, j in enumerate(g[f'{tag}_jhat']):
+        loss, grad = tr.meta_step(cu(y[j - 1:j]), cu(tx[j - 1:j]), cu(y[j:j + 1]), cu(tx[j:j + 1]),
+                                  second_order=second, return_grad=True)
+        ref_loss = g[f'{tag}_loss_q'][step]
+        assert abs(float(loss[0]) - ref_loss) < 1e-5 * abs(ref_loss)
+        if step == 0:
+            gr = grad[0].cpu().numpy()
+            o = 0
+            for i in range(6):
+                ref = g[f'{tag}_g1_{i}'].reshape(-1)
+                assert np.max(np.abs(gr[o:o + ref.size] - ref)) < 2e-5 * np.max(np.abs(ref)) + 1e-9
+                o += ref.size
+        assert_close_params(tr.theta[0].cpu().numpy(), [g[f'{tag}_w{step + 1}_{i}'] for i in range(6)], 2e-5)
+    assert tr.adam_step.tolist() == [3]
+
+
+def test_train_steps_match_reference_run(mvn):
+    g = load_golden('meta')
+    w0 = [g[f'sgd_w0_{i}'] for i in range(6)]
+    tr = mvn.BatchedVNetTrainer(cu(pack(w0)), 4, lr=1e-3)
+    for step in range(5):
+        loss = tr.train_step(cu(g['sgd_y']), cu(g['sgd_tx']))
+        assert abs(float(loss[0]) - g['sgd_losses'][step]) < 1e-5 * abs(g['sgd_losses'][step])
+    assert_close_params(tr.theta[0].cpu().numpy(), [g[f'sgd_w5_{i}'] for i in range(6)], 2e-5)
+
+
+@pytest.mark.parametrize('L', [2, 3, 4, 5])
+def test_batched_realisations_vs_oracle(mvn, L):
+    """R realisations with different weights/data; N > 256 symbols exercises the blocked symbol loop."""
+    rng = np.random.RandomState(L)
+    S, R, Ns, Nq = 2 ** L, 5, 300, 136
+    thetas, data = [], []
+    for r in range(R):
+        w = [rng.randn(100, 1) * .7, rng.randn(100) * .5, rng.randn(50, 100) * .15, rng.randn(50) * .1,
+             rng.randn(S, 50) * .3, rng.randn(S) * .1]
+        thetas.append([a.astype(np.float32) for a in w])
+        data.append((rng.randn(1, Ns).astype(np.float32) * 1.5, rng.randint(0, 2, (1, Ns)).astype(np.float32),
+                     rng.randn(1, Nq).astype(np.float32) * 1.5, rng.randint(0, 2, (1, Nq)).astype(np.float32)))
+    theta0 = np.stack([pack(w) for w in thetas])
+    ys, txs, yq, txq = [np.concatenate([d[i] for d in data]) for i in range(4)]
+    for second in (True, False):
+        tr = mvn.BatchedVNetTrainer(cu(theta0), L, lr=1e-3, meta_lr=0.1)
+        loss, grad = tr.meta_step(cu(ys), cu(txs), cu(yq), cu(txq), second_order=second, return_grad=True)
+        for r in range(R):
+            lq, mg, new_w, _ = orc.maml_step(*data[r], thetas[r], None, L, meta_lr=0.1, lr=1e-3, second_order=second)
+            assert abs(float(loss[r]) - lq) < 1e-5 * abs(lq)
+            ref = np.concatenate([a.reshape(-1) for a in mg])
+            assert np.max(np.abs(grad[r].cpu().numpy() - ref)) < 2e-5 * np.max(np.abs(ref))
+            assert_close_params(tr.theta[r].cpu().numpy(), new_w, 3e-5)
+    tr = mvn.BatchedVNetTrainer(cu(theta0), L, lr=1e-3)
+    state = [None] * R
+    ws = [list(w) for w in thetas]
+    for it in range(3):
+        loss = tr.train_step(cu(ys), cu(txs))
+        for r in range(R):
+            l, ws[r], state[r] = orc.train_step(data[r][0], data[r][1], ws[r], state[r], L, lr=1e-3)
+            assert abs(float(loss[r]) - l) < 1e-5 * abs(l)
+    for r in range(R):
+        assert_close_params(tr.theta[r].cpu().numpy(), ws[r], 3e-5)
+
+
+def test_train_phase_autograd_matches_torch(mvn):
+    """VNETDetector(y,'train') -> CE loss -> backward gives the gradients torch computes for the same net."""
+    g = load_golden('meta')
+    w0 = [g[f'sgd_w0_{i}'] for i in range(6)]
+    y, tx = g['sgd_y'], g['sgd_tx']
+    det = mvn.VNETDetector(16, {'val': y.shape[1], 'train': y.shape[1]})
+    with torch.no_grad():
+        for p, a in zip(det.parameters(), w0):
+            p.copy_(cu(a))
+    labels = mvn.calculate_states(4, cu(tx))
+    soft = det(cu(y), 'train')
+    loss = torch.nn.CrossEntropyLoss()(soft.reshape(-1, 16), labels)
+    loss.backward()
+    ref_loss, ref_g, _ = orc.loss_and_grads(y.reshape(-1), orc.calculate_states(4, tx), w0)
+    assert abs(float(loss) - ref_loss) < 1e-5 * abs(ref_loss)
+    for p, r in zip(det.parameters(), ref_g):
+        assert np.max(np.abs(p.grad.cpu().numpy().reshape(-1) - r.reshape(-1))) < 2e-5 * np.max(np.abs(r)) + 1e-9
+    # the reference's own optimiser on top of our gradients reproduces its first recorded step
+    opt = torch.optim.Adam(det.parameters(), lr=1e-3)
+    opt.step()
+    assert abs(float(loss) - g['sgd_losses'][0]) < 1e-5 * abs(g['sgd_losses'][0])
+    # functional detector (FO-MAML path: create_graph=False)
+    meta = mvn.META_VNETDetector(16, {'val': y.shape[1], 'train': y.shape[1]})
+    var = [cu(a).requires_grad_(True) for a in w0]
+    out = meta(cu(y), 'train', var)
+    gr = torch.autograd.grad(torch.nn.CrossEntropyLoss()(out.reshape(-1, 16), labels), var)
+    for a, r in zip(gr, ref_g):
+        assert np.max(np.abs(a.cpu().numpy().reshape(-1) - r.reshape(-1))) < 2e-5 * np.max(np.abs(r)) + 1e-9
+
+
+def test_training_rejects_unsupported_trellis(mvn):
+    with pytest.raises(mvn.MVNError):
+        mvn.BatchedVNetTrainer(torch.zeros(1, mvn.train.param_count(7)).cuda(), 7)
