@@ -45,7 +45,7 @@ template <int L>
 using TrellisFor = typename std::conditional<(L <= 5), RegTrellis<L>, SmemTrellis<L>>::type;
 
 template <int L, int NT>
-__global__ void __launch_bounds__(NT) acs_decode_kernel(AcsParams p) {
+__global__ void __launch_bounds__(NT, (L <= 5) ? 4 : 1) acs_decode_kernel(AcsParams p) {
     using D = TrellisDims<L>;
     constexpr int S = D::S, H = D::H, C = D::C, NCH = D::NCH;
     constexpr int WARPS = NT / 32;
@@ -164,7 +164,7 @@ __device__ __forceinline__ float va_cost(float y, float sp) {
 }
 
 template <int L, int NT>
-__global__ void __launch_bounds__(NT) va_decode_kernel(VaParams p) {
+__global__ void __launch_bounds__(NT, (L <= 5) ? 4 : 1) va_decode_kernel(VaParams p) {
     using D = TrellisDims<L>;
     constexpr int S = D::S, C = D::C, NCH = D::NCH;
     constexpr int WARPS = NT / 32;

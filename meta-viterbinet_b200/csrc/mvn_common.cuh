@@ -39,16 +39,19 @@ int sm_count();
 constexpr int kTileLd = 36;
 constexpr int kTileFloats = 32 * kTileLd;
 
+// Plain read-only loads: with L1::no_allocate the lines take the L2 evict-first class, and the second
+// 32-byte sector of each 64-byte DRAM fetch (rows are 480 B, tiles 128 B) is dropped before the next
+// tile of the same rows wants it — ncu showed 1.75x the algorithmic DRAM reads (profiles/r01).
 __device__ __forceinline__ float4 ldg_stream4(const float *p) {
     float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                  : "l"(p));
     return v;
 }
 __device__ __forceinline__ float ldg_stream1(const float *p) {
     float v;
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
 }
 

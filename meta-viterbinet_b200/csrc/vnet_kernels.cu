@@ -16,6 +16,13 @@
 
 #include "mvn_common.cuh"
 
+// Constant-bank weight slots.  C linkage so that inline PTX can name the symbol.
+constexpr int kConstSlotFloats = 7168;
+extern "C" {
+__constant__ float mvn_cParams[2 * kConstSlotFloats];
+__device__ float mvn_gStage[2 * kConstSlotFloats];
+}
+
 namespace mvn {
 
 typedef unsigned long long u64;
@@ -60,6 +67,59 @@ __device__ __forceinline__ float2 lds64f(uint32_t addr) {
     asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a.x), "=f"(a.y) : "r"(addr));
     return a;
 }
+
+// ------------------------------------------------------------------ weight sources
+// kSmem : staged layout in shared memory, warp-uniform (broadcast) LDS.64/.128.
+// kConst: staged layout in the constant bank; warp-uniform addresses make ptxas fetch the weights
+//         with LDCU into UNIFORM registers that FFMA2 takes directly as an operand, so the weight
+//         stream costs no vector registers, no LSU wavefronts and no RF write ports.
+//         (memory_length <= 5: two 28 KB slots of the 64 KB bank, used round-robin per call.)
+enum WeightSrc { kSmem = 0, kConst = 1 };
+
+// Volatile asm like the shared-memory loads (no hoisting out of the stage loop); the address is
+// warp-uniform (const-space address of cParams + slot + immediate), which is what lets ptxas pick LDCU.
+__device__ __forceinline__ u64 ldc64(uint32_t addr) {
+    u64 a;
+    asm volatile("ld.const.b64 %0, [%1];" : "=l"(a) : "r"(addr));
+    return a;
+}
+__device__ __forceinline__ float2 ldc64f(uint32_t addr) {
+    float2 a;
+    asm volatile("ld.const.v2.f32 {%0, %1}, [%2];" : "=f"(a.x), "=f"(a.y) : "r"(addr));
+    return a;
+}
+__device__ __forceinline__ uint32_t const_params_addr() {
+    uint32_t a;
+    asm("mov.u32 %0, mvn_cParams;" : "=r"(a));
+    return a;
+}
+
+template <int WS>
+struct Wt {
+    uint32_t base;  // byte address of the staged block in shared (kSmem) or constant (kConst) space
+    __device__ __forceinline__ u64 pair(int off) const {
+        if constexpr (WS == kSmem) {
+            return lds64(base + 4 * off);
+        } else {
+            return ldc64(base + 4 * off);
+        }
+    }
+    __device__ __forceinline__ void quad(int off, u64 &a, u64 &b) const {
+        if constexpr (WS == kSmem) {
+            lds128(base + 4 * off, a, b);
+        } else {
+            a = pair(off);
+            b = pair(off + 2);
+        }
+    }
+    __device__ __forceinline__ float2 f2(int off) const {
+        if constexpr (WS == kSmem) {
+            return lds64f(base + 4 * off);
+        } else {
+            return ldc64f(base + 4 * off);
+        }
+    }
+};
 
 // ------------------------------------------------------------------ staged weights
 #ifndef MVN_K_UNROLL
@@ -106,45 +166,45 @@ __device__ void stage_weights(float *sm, const VnetWeights &w, int tid, int nt) 
 }
 
 // ------------------------------------------------------------------ the MLP, M samples per lane
-template <int M>
-__device__ __forceinline__ void sigmoid_unit(uint32_t w1b1, int k, const float (&y)[M], float (&h)[M]) {
-    const float2 wb = lds64f(w1b1 + 8 * k);
+template <int M, int WS>
+__device__ __forceinline__ void sigmoid_unit(const Wt<WS> &wt, int k, const float (&y)[M], float (&h)[M]) {
+    const float2 wb = wt.f2(2 * k);  // oW1B1 == 0
 #pragma unroll
     for (int m = 0; m < M; m++) h[m] = rcp_approx(1.f + ex2_approx(fmaf(y[m], wb.x, wb.y)));
 }
 
 // layers 1+2 (+ReLU): y[M] -> h2[M][50]
-template <int L, int M>
-__device__ __forceinline__ void mlp_hidden(const float *sm, const float (&y)[M], float (&h2)[M][kH2]) {
+template <int L, int M, int WS, int KU>
+__device__ __forceinline__ void mlp_hidden(const Wt<WS> &wt, const float (&y)[M], float (&h2)[M][kH2]) {
     using W = VnetSmem<L>;
-    const uint32_t sa = smem_addr(sm);
+    static_assert(W::oW1B1 == 0, "sigmoid_unit assumes the (w1,b1) pairs lead the staged block");
     u64 acc[M][25];
 #pragma unroll
     for (int i = 0; i < 25; i++) {
-        const u64 b = lds64(sa + 4 * W::oB2 + 8 * i);
+        const u64 b = wt.pair(W::oB2 + 2 * i);
 #pragma unroll
         for (int m = 0; m < M; m++) acc[m][i] = b;
     }
     float hc[M], hn[M];
-    sigmoid_unit<M>(sa + 4 * W::oW1B1, 0, y, hc);
-#pragma unroll kKUnroll
+    sigmoid_unit<M, WS>(wt, 0, y, hc);
+#pragma unroll KU
     for (int k = 0; k < kH1; k++) {
-        sigmoid_unit<M>(sa + 4 * W::oW1B1, k + 1, y, hn);  // entry 100 is a zero pad
-        const uint32_t wr = sa + 4 * (W::oW2T + k * kW2Ld);
+        sigmoid_unit<M, WS>(wt, k + 1, y, hn);  // entry 100 is a zero pad
+        const int wr = W::oW2T + k * kW2Ld;
         u64 hh[M];
 #pragma unroll
         for (int m = 0; m < M; m++) hh[m] = pack2(hc[m], hc[m]);
 #pragma unroll
         for (int q = 0; q < 12; q++) {
             u64 wx, wy;
-            lds128(wr + 16 * q, wx, wy);
+            wt.quad(wr + 4 * q, wx, wy);
 #pragma unroll
             for (int m = 0; m < M; m++) {
                 ffma2_acc(acc[m][2 * q], hh[m], wx);
                 ffma2_acc(acc[m][2 * q + 1], hh[m], wy);
             }
         }
-        const u64 wl = lds64(wr + 16 * 12);
+        const u64 wl = wt.pair(wr + 48);
 #pragma unroll
         for (int m = 0; m < M; m++) ffma2_acc(acc[m][24], hh[m], wl);
 #pragma unroll
@@ -162,28 +222,27 @@ __device__ __forceinline__ void mlp_hidden(const float *sm, const float (&y)[M],
 }
 
 // layer 3 for output states [c*C, c*C + C): p[m][i] = b3 + sum_j h2[m][j] W3T[j][c*C+i]
-template <int L, int M>
-__device__ __forceinline__ void mlp_out_chunk(const float *sm, int c, const float (&h2)[M][kH2],
+template <int L, int M, int WS>
+__device__ __forceinline__ void mlp_out_chunk(const Wt<WS> &wt, int c, const float (&h2)[M][kH2],
                                               float (&p)[M][TrellisDims<L>::C]) {
     using W = VnetSmem<L>;
     constexpr int S = W::S, C = TrellisDims<L>::C, P = C / 2;
-    const uint32_t sa = smem_addr(sm);
     u64 acc[M][P];
 #pragma unroll
     for (int i = 0; i < P; i++) {
-        const u64 b = lds64(sa + 4 * (W::oB3 + c * C) + 8 * i);
+        const u64 b = wt.pair(W::oB3 + c * C + 2 * i);
 #pragma unroll
         for (int m = 0; m < M; m++) acc[m][i] = b;
     }
-    const uint32_t w3 = sa + 4 * (W::oW3T + c * C);
+    const int w3 = W::oW3T + c * C;
 #pragma unroll
     for (int j = 0; j < kH2; j++) {
         u64 w[P];
         if constexpr (C >= 4) {
 #pragma unroll
-            for (int i = 0; i < C / 4; i++) lds128(w3 + 4 * (j * S + 4 * i), w[2 * i], w[2 * i + 1]);
+            for (int i = 0; i < C / 4; i++) wt.quad(w3 + j * S + 4 * i, w[2 * i], w[2 * i + 1]);
         } else {
-            w[0] = lds64(w3 + 4 * (j * S));
+            w[0] = wt.pair(w3 + j * S);
         }
 #pragma unroll
         for (int m = 0; m < M; m++) {
@@ -209,6 +268,7 @@ __global__ void __launch_bounds__(NT) vnet_priors_kernel(const float *__restrict
     extern __shared__ __align__(16) float smem[];
     stage_weights<L>(smem, w, threadIdx.x, NT);
     __syncthreads();
+    const Wt<kSmem> wt{smem_addr(smem)};
     const int lane = threadIdx.x & 31;
     const int64_t n_warps = (int64_t(gridDim.x) * NT) >> 5;
     for (int64_t base = ((int64_t(blockIdx.x) * NT + threadIdx.x) >> 5) * 64; base < N; base += n_warps * 64) {
@@ -220,10 +280,10 @@ __global__ void __launch_bounds__(NT) vnet_priors_kernel(const float *__restrict
             yv[m] = n[m] < N ? y[n[m]] : 0.f;
         }
         float h2[M][kH2];
-        mlp_hidden<L, M>(smem, yv, h2);
+        mlp_hidden<L, M, kSmem, kKUnroll>(wt, yv, h2);
         for (int c = 0; c < NCH; c++) {
             float p[M][C];
-            mlp_out_chunk<L, M>(smem, c, h2, p);
+            mlp_out_chunk<L, M, kSmem>(wt, c, h2, p);
 #pragma unroll
             for (int m = 0; m < M; m++) {
                 if (n[m] < N) {
@@ -242,6 +302,12 @@ __global__ void __launch_bounds__(NT) vnet_priors_kernel(const float *__restrict
     }
 }
 
+// writes the staged layout into the global staging slot (constant-bank path)
+template <int L>
+__global__ void stage_weights_kernel(VnetWeights w, int slot) {
+    stage_weights<L>(mvn_gStage + slot * kConstSlotFloats, w, threadIdx.x, blockDim.x);
+}
+
 // =====================================================================================
 // a6+a3 fused
 // =====================================================================================
@@ -257,34 +323,47 @@ struct VnetParams {
     int target_T, pilot_period;
     unsigned long long *counters;
     int64_t n_warp_tiles;  // tiles of 32*M frames
+    int const_slot;
 };
 
-template <int L>
-struct FusedCfg {
+// Variant = (frames per lane, weight source, threads per CTA, layer-2 unroll).  One CTA per SM.
+template <int L, int M_, int WS_, int NT_, int KU_>
+struct FusedVariant {
+    static constexpr int M = M_, WS = WS_, NT = NT_, KU = KU_;
     static constexpr bool kRegPm = (L <= 4);
-    static constexpr int M = (L <= 7) ? 2 : 1;
-    static constexpr int NT = (L <= 5) ? 256 : 128;
+    static constexpr size_t smem_bytes() {
+        size_t fl = (WS == kSmem ? VnetSmem<L>::kFloats : 0) + size_t(NT / 32) * M * kTileFloats;
+        size_t bytes = fl * sizeof(float);
+        if (!kRegPm) bytes += SmemTrellis<L>::bytes(NT * M);
+        return bytes;
+    }
 };
 
-template <int L>
-__global__ void __launch_bounds__(FusedCfg<L>::NT, 1) vnet_decode_kernel(VnetParams p) {
+template <int L, class V>
+__global__ void __launch_bounds__(V::NT, 1) vnet_decode_kernel(VnetParams p) {
     using D = TrellisDims<L>;
-    using Cfg = FusedCfg<L>;
     using W = VnetSmem<L>;
-    constexpr int S = D::S, C = D::C, NCH = D::NCH, M = Cfg::M, NT = Cfg::NT;
+    constexpr int S = D::S, C = D::C, NCH = D::NCH, M = V::M, NT = V::NT, WS = V::WS;
     constexpr int WARPS = NT / 32;
-    using Tr = typename std::conditional<Cfg::kRegPm, RegTrellis<L>, SmemTrellis<L>>::type;
+    constexpr int kWFloats = (WS == kSmem) ? W::kFloats : 0;
+    using Tr = typename std::conditional<V::kRegPm, RegTrellis<L>, SmemTrellis<L>>::type;
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float *tiles = smem + W::kFloats + warp * (M * kTileFloats);
+    float *tiles = smem + kWFloats + warp * (M * kTileFloats);
 
-    stage_weights<L>(smem, p.w, threadIdx.x, NT);
-    __syncthreads();
+    Wt<WS> wt;
+    if constexpr (WS == kSmem) {
+        stage_weights<L>(smem, p.w, threadIdx.x, NT);
+        __syncthreads();
+        wt.base = smem_addr(smem);
+    } else {
+        wt.base = const_params_addr() + uint32_t(p.const_slot * kConstSlotFloats * 4);
+    }
 
     Tr tr[M];
-    if constexpr (!Cfg::kRegPm) {
+    if constexpr (!V::kRegPm) {
 #pragma unroll
-        for (int m = 0; m < M; m++) tr[m].init(smem + W::kFloats + WARPS * M * kTileFloats, NT * M, m * NT + threadIdx.x);
+        for (int m = 0; m < M; m++) tr[m].init(smem + kWFloats + WARPS * M * kTileFloats, NT * M, m * NT + threadIdx.x);
     }
 
     const bool vec_in = is_vec_ok(p.y, p.T, p.T);
@@ -293,8 +372,12 @@ __global__ void __launch_bounds__(FusedCfg<L>::NT, 1) vnet_decode_kernel(VnetPar
     const int n_words = (p.T + 31) / 32;
     ErrAcc acc;
 
-    for (int64_t wt = int64_t(blockIdx.x) * WARPS + warp; wt < p.n_warp_tiles; wt += int64_t(gridDim.x) * WARPS) {
-        const int64_t row0 = wt * (32 * M);
+    // CTA-uniform trip count (all warps of a CTA run the same number of tiles, out-of-range frames are
+    // masked): keeps the control flow provably warp-uniform, which the uniform datapath (LDCU, UR
+    // operands) of the constant-bank variants requires.
+    const int64_t n_cta_tiles = (p.n_warp_tiles + WARPS - 1) / WARPS;
+    for (int64_t ct = blockIdx.x; ct < n_cta_tiles; ct += gridDim.x) {
+        const int64_t row0 = (ct * WARPS + warp) * (32 * M);
         unsigned frame_bit_errs[M];
 #pragma unroll
         for (int m = 0; m < M; m++) {
@@ -310,18 +393,19 @@ __global__ void __launch_bounds__(FusedCfg<L>::NT, 1) vnet_decode_kernel(VnetPar
 #pragma unroll
                 for (int m = 0; m < M; m++)
                     warp_load_tile(p.y, p.B, p.T, p.T, row0 + 32 * m, t0, tiles + m * kTileFloats, lane, vec_in);
+#pragma unroll 1
                 for (int tt = 0; tt < t_end; tt++) {
                     float yv[M];
 #pragma unroll
                     for (int m = 0; m < M; m++) yv[m] = tiles[m * kTileFloats + lane * kTileLd + tt];
                     float h2[M][kH2];
-                    mlp_hidden<L, M>(smem, yv, h2);
+                    mlp_hidden<L, M, WS, V::KU>(wt, yv, h2);
 #pragma unroll
                     for (int m = 0; m < M; m++) bits[m] |= tr[m].decide() << tt;
-                    if constexpr (Cfg::kRegPm) {
-                        static_assert(!Cfg::kRegPm || NCH == 1, "register trellis in the fused kernel: S <= 16");
+                    if constexpr (V::kRegPm) {
+                        static_assert(!V::kRegPm || NCH == 1, "register trellis in the fused kernel: S <= 16");
                         float pr[M][C];
-                        mlp_out_chunk<L, M>(smem, 0, h2, pr);
+                        mlp_out_chunk<L, M, WS>(wt, 0, h2, pr);
 #pragma unroll
                         for (int m = 0; m < M; m++) {
                             float cost[C];
@@ -339,7 +423,7 @@ __global__ void __launch_bounds__(FusedCfg<L>::NT, 1) vnet_decode_kernel(VnetPar
                     } else {
                         for (int c = 0; c < NCH; c++) {
                             float pr[M][C];
-                            mlp_out_chunk<L, M>(smem, c, h2, pr);
+                            mlp_out_chunk<L, M, WS>(wt, c, h2, pr);
 #pragma unroll
                             for (int m = 0; m < M; m++) {
                                 float cost[C];
@@ -395,28 +479,56 @@ __global__ void __launch_bounds__(FusedCfg<L>::NT, 1) vnet_decode_kernel(VnetPar
     }
 }
 
-template <int L>
-static size_t fused_smem_bytes() {
-    using Cfg = FusedCfg<L>;
-    size_t fl = VnetSmem<L>::kFloats + size_t(Cfg::NT / 32) * Cfg::M * kTileFloats;
-    size_t bytes = fl * sizeof(float);
-    if (!Cfg::kRegPm) bytes += SmemTrellis<L>::bytes(Cfg::NT * Cfg::M);
-    return bytes;
-}
+static int g_variant = 0;       // tuning knob for memory_length 4 (mvn_debug_set_variant)
+static int g_const_slot = 0;
 
-template <int L>
-static int launch_fused(const VnetParams &p, cudaStream_t st) {
-    using Cfg = FusedCfg<L>;
-    const size_t smem = fused_smem_bytes<L>();
-    auto kern = vnet_decode_kernel<L>;
+template <int L, class V>
+static int launch_variant(VnetParams p, cudaStream_t st) {
+    const size_t smem = V::smem_bytes();
+    auto kern = vnet_decode_kernel<L, V>;
     MVN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    const int warps = Cfg::NT / 32;
+    p.n_warp_tiles = (p.B + 32 * V::M - 1) / (32 * V::M);
+    if (V::WS == kConst) {
+        static_assert(V::WS != kConst || VnetSmem<L>::kFloats <= kConstSlotFloats, "constant slot too small");
+        const int slot = (g_const_slot++) & 1;
+        p.const_slot = slot;
+        stage_weights_kernel<L><<<1, 256, 0, st>>>(p.w, slot);
+        note_launch();
+        void *src = nullptr;
+        MVN_CUDA(cudaGetSymbolAddress(&src, mvn_gStage));
+        MVN_CUDA(cudaMemcpyToSymbolAsync(mvn_cParams, static_cast<float *>(src) + slot * kConstSlotFloats,
+                                         VnetSmem<L>::kFloats * sizeof(float),
+                                         size_t(slot) * kConstSlotFloats * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    const int warps = V::NT / 32;
     const int64_t need = (p.n_warp_tiles + warps - 1) / warps;
     const int grid = int(std::min<int64_t>(need, sm_count()));
-    kern<<<grid, Cfg::NT, smem, st>>>(p);
+    kern<<<grid, V::NT, smem, st>>>(p);
     note_launch();
     MVN_CUDA(cudaGetLastError());
     return MVN_OK;
+}
+
+// Default variants, picked by tools/tune_fused.py on a B200 (profiles/r01_tune_fused.txt):
+//   L <= 5: constant-bank weights, 2 frames per lane, 384 threads (3 warps per scheduler), unroll 10
+//   L 6..7: staged weights in shared memory (the constant bank is too small for W3), 128 threads
+//   L = 8 : as above with one frame per lane (the path metrics take 131 KB of shared memory)
+template <int L>
+static int launch_fused(const VnetParams &p, cudaStream_t st) {
+    if constexpr (L <= 5) {
+        switch (g_variant) {
+            case 1: return launch_variant<L, FusedVariant<L, 2, kSmem, 256, 10>>(p, st);
+            case 2: return launch_variant<L, FusedVariant<L, 2, kSmem, 256, 5>>(p, st);
+            case 3: return launch_variant<L, FusedVariant<L, 2, kConst, 384, 20>>(p, st);
+            case 4: return launch_variant<L, FusedVariant<L, 2, kConst, 320, 10>>(p, st);
+            case 5: return launch_variant<L, FusedVariant<L, 2, kConst, 448, 10>>(p, st);
+            default: return launch_variant<L, FusedVariant<L, 2, kConst, 384, 10>>(p, st);
+        }
+    } else if constexpr (L <= 7) {
+        return launch_variant<L, FusedVariant<L, 2, kSmem, 128, 5>>(p, st);
+    } else {
+        return launch_variant<L, FusedVariant<L, 1, kSmem, 128, 5>>(p, st);
+    }
 }
 
 template <int L>
@@ -454,7 +566,6 @@ int vnet_decode_impl(const VnetParams &p, int L, cudaStream_t st) { MVN_DISPATCH
 int vnet_priors_impl(const float *y, int64_t N, int L, const VnetWeights &w, float *priors, cudaStream_t st) {
     MVN_DISPATCH_L(L, launch_priors, y, N, w, priors, st)
 }
-int vnet_frames_per_warp_tile(int L) { return L <= 7 ? 64 : 32; }
 
 }  // namespace mvn
 
@@ -498,8 +609,14 @@ extern "C" int mvn_vnet_decode(const float *y, int64_t B, int T, int L, int n_st
         return MVN_ERR_ARG;
     }
     if (B == 0 || T == 0) return MVN_OK;
-    const int fpt = vnet_frames_per_warp_tile(L);
     VnetParams p{y, B, T, n_stages, VnetWeights{w1, b1, w2, b2, w3, b3}, out_format, decoded, priors_out, target,
-                 target_T, pilot_period, reinterpret_cast<unsigned long long *>(counters), (B + fpt - 1) / fpt};
+                 target_T, pilot_period, reinterpret_cast<unsigned long long *>(counters), 0, 0};
     return vnet_decode_impl(p, L, static_cast<cudaStream_t>(stream));
+}
+
+// Tuning knob (not part of the public header): selects the fused-kernel variant for memory_length 4.
+extern "C" int mvn_debug_set_variant(int v) {
+    const int old = g_variant;
+    g_variant = v;
+    return old;
 }

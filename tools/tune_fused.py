@@ -1,0 +1,41 @@
+"""Times every fused-kernel variant (mvn_debug_set_variant) on the bench workload and checks that all of
+them produce identical bits.  Usage (GPU box): python tools/tune_fused.py [frames]"""
+import ctypes
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import bench
+import meta_viterbinet_b200 as mvn
+from meta_viterbinet_b200 import _lib
+
+frames = int(sys.argv[1]) if len(sys.argv) > 1 else bench.FRAMES
+dev = torch.device('cuda', 0)
+w = bench.make_weights(torch, dev)
+bits, y = bench.synth_frames(torch, dev, frames, 10, 1)
+lib = _lib.load()
+lib.mvn_debug_set_variant.restype = ctypes.c_int
+lib.mvn_debug_set_variant.argtypes = [ctypes.c_int]
+names = {0: 'const M2 384 u10 (default)', 1: 'smem M2 256 u10', 2: 'smem M2 256 u5', 3: 'const M2 384 u20',
+         4: 'const M2 320 u10', 5: 'const M2 448 u10'}
+ref = None
+for v in sorted(names):
+    lib.mvn_debug_set_variant(v)
+    out = mvn.ops.vnet_decode(y, w)
+    torch.cuda.synchronize()
+    if ref is None:
+        ref = out
+    same = bool(torch.equal(out, ref))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        mvn.ops.vnet_decode(y, w)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    rate = frames * bench.T / ms / 1e6
+    print(f'variant {v} [{names[v]:26s}] {ms:8.3f} ms  {rate:7.3f} Gsym/s  {rate * bench.FLOP_PER_SYMBOL / 1e3:6.2f} TFLOP/s  '
+          f'bits_equal_to_v0={same}', flush=True)
+lib.mvn_debug_set_variant(0)
