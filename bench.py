@@ -270,7 +270,7 @@ def main():
     y_host = y.cpu().pin_memory()
     out_host = torch.empty_like(y_host).pin_memory()
     ctx = ctypes.c_void_p()
-    _lib.check(lib.mvn_ctx_create(ctypes.byref(ctx), local, 1 << 16, T, MEMORY_LENGTH))
+    _lib.check(lib.mvn_ctx_create(ctypes.byref(ctx), local, 0, T, MEMORY_LENGTH))
     w_host = [w.cpu().contiguous() for w in weights]
     _lib.check(lib.mvn_ctx_set_vnet_weights_host(ctx, *[ctypes.c_void_p(w.data_ptr()) for w in w_host]))
 
@@ -350,7 +350,7 @@ def main():
             'roofline': roofline, 'cpu_baseline': cpu_baseline,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': frames * T * 4 * world,
                     'd2h_bytes_per_step': frames * T * 4 * world, 'matches_device_path': e2e_ok,
-                    'api': 'mvn_ctx_vnet_decode_host (pinned host buffers, 65536-frame chunks, 2 streams)'},
+                    'api': 'mvn_ctx_vnet_decode_host (pinned host buffers, chunks of two kernel waves, 2 streams)'},
             'gpu_launches': launches, 'clocks': clocks,
             'ber': {'bit_errors': be, 'frame_errors': fe, 'bits': nb, 'frames': nf,
                     'note': 'untrained (random-init) weights: BER is ~0.5 by construction'},

@@ -107,6 +107,7 @@ int mvn_error_counts(const float *prediction, int pred_stride, const float *targ
  * pipeline on the context's own streams and device buffers.  This is what bench.py's `e2e`
  * times.  y_host [B,T] fp32 -> decoded_host (out_format).  Weights are host pointers too. */
 typedef struct mvn_ctx mvn_ctx;
+/* chunk_frames <= 0 selects two full waves of the fused kernel per chunk. */
 int mvn_ctx_create(mvn_ctx **ctx, int device, int64_t chunk_frames, int T_max, int L);
 void mvn_ctx_destroy(mvn_ctx *ctx);
 int mvn_ctx_set_vnet_weights_host(mvn_ctx *ctx, const float *w1, const float *b1, const float *w2,

@@ -175,7 +175,9 @@ __global__ void __launch_bounds__(NT, (L <= 5) ? 4 : 1) va_decode_kernel(VaParam
     float *ttile = tile + kTileFloats;
     const float *row = tile + lane * kTileLd;
 
-    TrellisFor<L> tr;
+    constexpr bool PACKED = (L >= 2 && L <= 5);
+    using Tr = typename std::conditional<PACKED, PackedTrellis<PACKED ? L : 2>, TrellisFor<L>>::type;
+    Tr tr;
     if constexpr (L > 5) tr.init(smem + WARPS * 2 * kTileFloats, NT, threadIdx.x);
 
     const bool vec_in = is_vec_ok(p.y, p.T, p.T);
@@ -188,8 +190,12 @@ __global__ void __launch_bounds__(NT, (L <= 5) ? 4 : 1) va_decode_kernel(VaParam
         const int64_t row0 = wt * 32;
         const int64_t b = row0 + lane;
         const float *sp_row = p.sp + int64_t((b < p.B ? b : 0) % p.n_h) * S;
-        float sp[SP_REGS ? S : 1];
-        if constexpr (SP_REGS) {
+        float sp[(SP_REGS && !PACKED) ? S : 1];
+        u64_t nsp2[PACKED ? S / 2 : 1];  // (-sp[2i], -sp[2i+1]): y - sp == y + (-sp) exactly
+        if constexpr (PACKED) {
+#pragma unroll
+            for (int i = 0; i < S / 2; i++) nsp2[i] = pk2(-__ldg(sp_row + 2 * i), -__ldg(sp_row + 2 * i + 1));
+        } else if constexpr (SP_REGS) {
 #pragma unroll
             for (int s = 0; s < S; s++) sp[s] = __ldg(sp_row + s);
         }
@@ -203,7 +209,18 @@ __global__ void __launch_bounds__(NT, (L <= 5) ? 4 : 1) va_decode_kernel(VaParam
                 for (int tt = 0; tt < t_end; tt++) {
                     const float yv = row[tt];
                     bits |= tr.decide() << tt;
-                    if constexpr (SP_REGS) {
+                    if constexpr (PACKED) {
+                        // d = y*1 + (-sp) (one rounding, == y - sp); sq = d*d; cost = sq*0.5 - ln sqrt(2 pi)
+                        const u64_t yy = pk2(yv, yv), one2 = pk2(1.f, 1.f), half2 = pk2(0.5f, 0.5f);
+                        const u64_t negk2 = pk2(-kLogSqrt2Pi, -kLogSqrt2Pi);
+                        u64_t cost2[S / 2];
+#pragma unroll
+                        for (int i = 0; i < S / 2; i++) {
+                            const u64_t d2 = fma2(yy, one2, nsp2[i]);
+                            cost2[i] = fma2(mul2(d2, d2), half2, negk2);
+                        }
+                        tr.step(cost2);
+                    } else if constexpr (SP_REGS) {
                         float c0[C];
 #pragma unroll
                         for (int i = 0; i < C; i++) c0[i] = va_cost(yv, sp[i]);
@@ -228,7 +245,7 @@ __global__ void __launch_bounds__(NT, (L <= 5) ? 4 : 1) va_decode_kernel(VaParam
                             tr.step_chunk_rt(c, cc);
                         }
                     }
-                    tr.commit();
+                    if constexpr (!PACKED) tr.commit();
                 }
                 __syncwarp();
             }

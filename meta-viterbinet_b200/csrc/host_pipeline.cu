@@ -24,14 +24,22 @@ struct mvn_ctx {
     bool have_w = false;
 };
 
+namespace mvn {
+int vnet_frames_per_wave(int L);
+}
 using namespace mvn;
 
 static int param_count(int S) { return kH1 + kH1 + kH2 * kH1 + kH2 + S * kH2 + S; }
 
 extern "C" int mvn_ctx_create(mvn_ctx **out, int device, int64_t chunk_frames, int T_max, int L) {
-    if (!out || chunk_frames < 1 || T_max < 1 || L < 1 || L > 8) {
+    if (!out || T_max < 1 || L < 1 || L > 8) {
         set_error("mvn_ctx_create: bad argument");
         return MVN_ERR_ARG;
+    }
+    if (chunk_frames <= 0) {  // auto: two full waves of the fused kernel per chunk
+        cudaError_t e0 = cudaSetDevice(device);
+        if (e0 != cudaSuccess) return cuda_fail(e0, "cudaSetDevice");
+        chunk_frames = 2 * int64_t(vnet_frames_per_wave(L));
     }
     mvn_ctx *c = new (std::nothrow) mvn_ctx();
     if (!c) {

@@ -223,6 +223,82 @@ struct SmemTrellis {
     __device__ __forceinline__ float metric(int h) const { return at(cur, h); }
 };
 
+// ---------------------------------------------------------------- packed fp32x2 helpers (sm_100)
+// add/mul/fma.rn.f32x2 round each half exactly like the scalar instruction, so bit-exactness with
+// the reference's fp32 arithmetic is preserved while the instruction count halves.
+typedef unsigned long long u64_t;
+__device__ __forceinline__ u64_t pk2(float a, float b) {
+    u64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void upk2(u64_t v, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ u64_t fma2(u64_t a, u64_t b, u64_t c) {
+    u64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64_t mul2(u64_t a, u64_t b) {
+    u64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64_t add2(u64_t a, u64_t b) {
+    u64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// Register trellis on fp32x2 pairs (2 <= L <= 5).  Source states 2i and 2i+1 are exactly the pair
+// (pm[2i mod H], pm[2i+1 mod H]) = pm2[i mod H/2], so one packed add serves both candidates of new
+// state i.  decide() uses the even/odd minima; only an exact tie between them (common at the first
+// stages and with integer costs, rare otherwise) takes the ordered scan.
+template <int L>
+struct PackedTrellis {
+    static constexpr int S = 1 << L, H = S / 2, HP = H / 2;
+    static_assert(L >= 2 && L <= 5, "packed trellis: 4..32 states");
+    u64_t pm2[HP];
+    __device__ __forceinline__ void reset() {
+#pragma unroll
+        for (int i = 0; i < HP; i++) pm2[i] = 0ull;
+    }
+    __device__ __forceinline__ uint32_t decide() const {
+        float v[H];
+#pragma unroll
+        for (int i = 0; i < HP; i++) upk2(pm2[i], v[2 * i], v[2 * i + 1]);
+        float e = v[0], o = v[1];
+#pragma unroll
+        for (int i = 1; i < HP; i++) {
+            e = fminf(e, v[2 * i]);
+            o = fminf(o, v[2 * i + 1]);
+        }
+        uint32_t bit = (o < e) ? 1u : 0u;
+        if (o == e) {  // lowest index among equal minima decides
+            float best = v[0];
+            bit = 0;
+#pragma unroll
+            for (int h = 1; h < H; h++) {
+                const bool lt = v[h] < best;
+                best = fminf(best, v[h]);
+                bit = lt ? uint32_t(h & 1) : bit;
+            }
+        }
+        return bit;
+    }
+    // cost2[i] = packed branch costs of source states (2i, 2i+1), i < H
+    __device__ __forceinline__ void step(const u64_t (&cost2)[H]) {
+        float nw[H];
+#pragma unroll
+        for (int i = 0; i < H; i++) {
+            float a, b;
+            upk2(add2(pm2[i % HP], cost2[i]), a, b);
+            nw[i] = fminf(a, b);
+        }
+#pragma unroll
+        for (int i = 0; i < HP; i++) pm2[i] = pk2(nw[2 * i], nw[2 * i + 1]);
+    }
+};
+
 // ---------------------------------------------------------------- fused BER/FER accounting
 struct ErrAcc {
     unsigned bit_errs = 0, frame_errs = 0, bits = 0, frames = 0;

@@ -12,6 +12,7 @@
 //   * sigmoid(a) = 1/(1+2^(-a log2 e)) with -log2 e folded into W1/b1 when the weights are staged:
 //     one FFMA + MUFU.EX2 + FADD + MUFU.RCP per hidden unit.
 #include <algorithm>
+#include <mutex>
 #include <type_traits>
 
 #include "mvn_common.cuh"
@@ -480,7 +481,16 @@ __global__ void __launch_bounds__(V::NT, 1) vnet_decode_kernel(VnetParams p) {
 }
 
 static int g_variant = 0;       // tuning knob for memory_length 4 (mvn_debug_set_variant)
-static int g_const_slot = 0;
+
+// The two constant-bank slots are the only state shared between calls.  Each slot carries an event
+// recorded after the kernel that read it; the next call that wants the slot makes its stream wait
+// on that event before overwriting it, so calls on different streams (and host threads) stay safe.
+struct ConstSlots {
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int next = 0;
+};
+static ConstSlots g_slots[64];
+static std::mutex g_slot_mu;
 
 template <int L, class V>
 static int launch_variant(VnetParams p, cudaStream_t st) {
@@ -488,10 +498,21 @@ static int launch_variant(VnetParams p, cudaStream_t st) {
     auto kern = vnet_decode_kernel<L, V>;
     MVN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     p.n_warp_tiles = (p.B + 32 * V::M - 1) / (32 * V::M);
+    const int warps = V::NT / 32;
+    const int64_t need = (p.n_warp_tiles + warps - 1) / warps;
+    const int grid = int(std::min<int64_t>(need, sm_count()));
     if (V::WS == kConst) {
         static_assert(V::WS != kConst || VnetSmem<L>::kFloats <= kConstSlotFloats, "constant slot too small");
-        const int slot = (g_const_slot++) & 1;
+        int dev = 0;
+        MVN_CUDA(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lock(g_slot_mu);
+        ConstSlots &cs = g_slots[dev & 63];
+        for (int i = 0; i < 2; i++)
+            if (!cs.ev[i]) MVN_CUDA(cudaEventCreateWithFlags(&cs.ev[i], cudaEventDisableTiming));
+        const int slot = cs.next;
+        cs.next ^= 1;
         p.const_slot = slot;
+        MVN_CUDA(cudaStreamWaitEvent(st, cs.ev[slot], 0));
         stage_weights_kernel<L><<<1, 256, 0, st>>>(p.w, slot);
         note_launch();
         void *src = nullptr;
@@ -499,10 +520,12 @@ static int launch_variant(VnetParams p, cudaStream_t st) {
         MVN_CUDA(cudaMemcpyToSymbolAsync(mvn_cParams, static_cast<float *>(src) + slot * kConstSlotFloats,
                                          VnetSmem<L>::kFloats * sizeof(float),
                                          size_t(slot) * kConstSlotFloats * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        kern<<<grid, V::NT, smem, st>>>(p);
+        note_launch();
+        MVN_CUDA(cudaGetLastError());
+        MVN_CUDA(cudaEventRecord(cs.ev[slot], st));
+        return MVN_OK;
     }
-    const int warps = V::NT / 32;
-    const int64_t need = (p.n_warp_tiles + warps - 1) / warps;
-    const int grid = int(std::min<int64_t>(need, sm_count()));
     kern<<<grid, V::NT, smem, st>>>(p);
     note_launch();
     MVN_CUDA(cudaGetLastError());
@@ -510,25 +533,36 @@ static int launch_variant(VnetParams p, cudaStream_t st) {
 }
 
 // Default variants, picked by tools/tune_fused.py on a B200 (profiles/r01_tune_fused.txt):
-//   L <= 5: constant-bank weights, 2 frames per lane, 384 threads (3 warps per scheduler), unroll 10
+//   L 4..5: constant-bank weights, 2 frames per lane, 384 threads (3 warps per scheduler), unroll 10
+//   L 1..3: same with 448 threads.  ptxas only routes the weight stream through uniform registers
+//           (LDCU) when vector registers are scarce; with the smaller layer-3 tile of these trellises
+//           the 384-thread build falls back to per-lane LDC, which is 2x slower.
+//           tools/check_sass.py asserts LDCU in the hot loop of every default variant.
 //   L 6..7: staged weights in shared memory (the constant bank is too small for W3), 128 threads
 //   L = 8 : as above with one frame per lane (the path metrics take 131 KB of shared memory)
 template <int L>
 static int launch_fused(const VnetParams &p, cudaStream_t st) {
-    if constexpr (L <= 5) {
+    if constexpr (L <= 3) {
+        return launch_variant<L, FusedVariant<L, 2, kConst, 448, 10>>(p, st);
+    } else if constexpr (L == 4) {
         switch (g_variant) {
             case 1: return launch_variant<L, FusedVariant<L, 2, kSmem, 256, 10>>(p, st);
-            case 2: return launch_variant<L, FusedVariant<L, 2, kSmem, 256, 5>>(p, st);
-            case 3: return launch_variant<L, FusedVariant<L, 2, kConst, 384, 20>>(p, st);
-            case 4: return launch_variant<L, FusedVariant<L, 2, kConst, 320, 10>>(p, st);
-            case 5: return launch_variant<L, FusedVariant<L, 2, kConst, 448, 10>>(p, st);
+            case 2: return launch_variant<L, FusedVariant<L, 2, kConst, 320, 10>>(p, st);
             default: return launch_variant<L, FusedVariant<L, 2, kConst, 384, 10>>(p, st);
         }
+    } else if constexpr (L == 5) {
+        return launch_variant<L, FusedVariant<L, 2, kConst, 384, 10>>(p, st);
     } else if constexpr (L <= 7) {
         return launch_variant<L, FusedVariant<L, 2, kSmem, 128, 5>>(p, st);
     } else {
         return launch_variant<L, FusedVariant<L, 1, kSmem, 128, 5>>(p, st);
     }
+}
+
+// frames decoded by one full wave of CTAs (host pipeline chunk sizing)
+int vnet_frames_per_wave(int L) {
+    const int per_cta = L <= 3 ? 448 * 2 : L <= 5 ? 384 * 2 : L <= 7 ? 128 * 2 : 128;
+    return per_cta * sm_count();
 }
 
 template <int L>

@@ -396,3 +396,56 @@ def test_full_size_properties(mvn):
     assert torch.equal(dec_big, dec_u[perm.cuda()])
     words = mvn.ops.vnet_decode(y, w, out_format=mvn.OUT_BITS)
     assert torch.equal(mvn.ops.unpack_bits(words[:5000], T), dec_big[:5000])
+
+
+# ------------------------------------------------------------------------------- shared state / sweeps
+def test_constant_slots_are_safe_across_streams(mvn):
+    """The fused kernel keeps its weights in two constant-bank slots; interleaved calls with DIFFERENT
+    weights on different streams must not see each other's weights."""
+    rng = np.random.RandomState(5)
+    y = cu((rng.randn(3000, 64) * 1.5).astype(np.float32))
+    sets = []
+    for k in range(3):
+        w = [rng.randn(100, 1) * .7, rng.randn(100) * .5, rng.randn(50, 100) * .15, rng.randn(50) * .1,
+             rng.randn(16, 50) * .3, rng.randn(16) * .1]
+        sets.append([cu(a.astype(np.float32)) for a in w])
+    ref = [mvn.ops.vnet_decode(y, w) for w in sets]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    outs = []
+    for rep in range(4):
+        for k, st in enumerate(streams):
+            with torch.cuda.stream(st):
+                outs.append((k, mvn.ops.vnet_decode(y, sets[k])))
+    torch.cuda.synchronize()
+    for k, o in outs:
+        assert torch.equal(o, ref[k])
+
+
+def test_sweep_on_gpu_counts(mvn):
+    g = load_golden('vnet')
+    w = [cu(a) for a in _w(g, 'trained_w')]
+    rng = np.random.RandomState(9)
+    data = {}
+    for snr in (8.0, 10.0):
+        bits = rng.randint(0, 2, size=(300, 120))
+        yy = orc.isi_awgn(bits, np.exp(-0.2 * np.arange(4)).reshape(1, 4), snr, 4, rng).astype(np.float32)
+        data[snr] = (cu(yy), cu(bits.astype(np.float32)))
+
+    def block(snr, first, n, row):
+        yy, bb = data[snr]
+        mvn.ops.vnet_decode(yy[first:first + n].contiguous(), w, target=bb[first:first + n].contiguous(), counters=row,
+                            want_decoded=False)
+
+    total = mvn.sweep.run_sweep([8.0, 10.0], 300, block, device='cuda')
+    for i, snr in enumerate((8.0, 10.0)):
+        yy, bb = data[snr]
+        dec = mvn.ops.vnet_decode(yy, w).cpu().numpy()
+        be, fe, nb, nf, _ = orc.error_counts(dec, bb.cpu().numpy())
+        assert total[i].tolist() == [be, fe, nb, nf]
+    # splitting a point into row blocks (more ranks than points) gives the same totals
+    parts = torch.zeros(2, 4, dtype=torch.int64, device='cuda')
+    for r in range(4):
+        c = mvn.sweep.run_sweep([8.0, 10.0], 300, block, device='cuda', rank=r, world_size=4)
+        parts += c
+    assert torch.equal(parts, total)
