@@ -5,6 +5,21 @@ from . import _lib
 from ._lib import OUT_BITS, OUT_F32, check, dev_f32, load, ptr, stream
 
 
+FUSED_VARIANTS = {'auto': 0, 'fma_smem': 1, 'fma_const_320': 2, 'tcgen05': 3, 'fma': 4}
+
+
+def set_fused_variant(name: str = 'auto') -> str:
+    """Select the implementation of the fused ViterbiNet kernel for memory_length 4 (tuning / testing):
+    'auto' (library default), 'tcgen05' (layer 2 on the tensor cores, bf16x6 split), 'fma' (FP32 FMA pipe,
+    constant-bank weights), 'fma_smem'.  Returns the previous selection."""
+    import ctypes
+    lib = load()
+    lib.mvn_debug_set_variant.restype = ctypes.c_int
+    lib.mvn_debug_set_variant.argtypes = [ctypes.c_int]
+    old = lib.mvn_debug_set_variant(FUSED_VARIANTS[name])
+    return {v: k for k, v in FUSED_VARIANTS.items()}.get(old, 'auto')
+
+
 def _mem_len(n_states: int) -> int:
     L = int(n_states).bit_length() - 1
     if n_states < 2 or (1 << L) != n_states:

@@ -29,6 +29,14 @@ def mvn():
     return m
 
 
+@pytest.fixture(params=['tcgen05', 'fma', 'fma_smem'])
+def fused_impl(request, mvn):
+    """Every fused-ViterbiNet parity test runs on the tensor-core variant and on the FP32-FMA variants."""
+    old = mvn.ops.set_fused_variant(request.param)
+    yield request.param
+    mvn.ops.set_fused_variant('auto')
+
+
 def cu(a):
     return torch.as_tensor(np.ascontiguousarray(a)).cuda()
 
@@ -211,14 +219,16 @@ def _explain_mismatches(dec_k, dec_ref, priors_ref, tol_rows):
 
 
 @pytest.mark.parametrize('tag', ['init', 'trained'])
-def test_vnet_fused_decode_golden(mvn, tag):
+def test_vnet_fused_decode_golden(mvn, fused_impl, tag):
     g = load_golden('vnet')
     w, y = _w(g, f'{tag}_w'), g['y']
     dec, pri = mvn.ops.vnet_decode(cu(y), [cu(a) for a in w], return_priors=True)
     dec, pri = dec.cpu().numpy(), pri.cpu().numpy()
     # priors exported by the fused kernel == the priors kernel (same arithmetic), within tolerance of torch
     pri2 = mvn.ops.vnet_priors(cu(y), [cu(a) for a in w]).cpu().numpy()
-    assert np.array_equal(pri.view(np.uint32), pri2.view(np.uint32))
+    if fused_impl != 'tcgen05':     # same FMA arithmetic -> identical bits; the tensor-core path differs by ~1e-7
+        assert np.array_equal(pri.view(np.uint32), pri2.view(np.uint32))
+    assert rel_to_rowmax(pri, pri2) < PRIOR_RTOL
     assert rel_to_rowmax(pri, g[f'{tag}_priors']) < PRIOR_RTOL
     # (i) reference loop on the kernel's own priors: bit-exact
     ref_own, _ = orc.vnet_decode_from_priors(pri)
@@ -228,11 +238,11 @@ def test_vnet_fused_decode_golden(mvn, tag):
     n_bad = _explain_mismatches(dec, g[f'{tag}_dec'], g[f'{tag}_priors'], tol)
     assert n_bad <= 1
     # small-batch path of the detector (priors kernel + ACS kernel) gives the same bits
-    dec_small = mvn.ops.acs_decode(-cu(pri2))
+    dec_small = mvn.ops.acs_decode(-cu(pri))
     assert np.array_equal(dec_small.cpu().numpy(), dec)
 
 
-def test_vnet_fused_loop_length(mvn):
+def test_vnet_fused_loop_length(mvn, fused_impl):
     g = load_golden('vnet')
     w, y = _w(g, 'trained_w'), g['y']
     dec = mvn.ops.vnet_decode(cu(y), [cu(a) for a in w], n_stages=100).cpu().numpy()
@@ -245,7 +255,7 @@ def test_vnet_fused_loop_length(mvn):
 
 @pytest.mark.parametrize('L', range(1, 9))
 @pytest.mark.parametrize('B,T', [(1, 7), (70, 33), (515, 40)])
-def test_vnet_fused_all_trellis_sizes(mvn, L, B, T):
+def test_vnet_fused_all_trellis_sizes(mvn, fused_impl, L, B, T):
     rng = np.random.RandomState(10 * L + B)
     S = 2 ** L
     w = [rng.randn(100, 1) * .7, rng.randn(100) * .5, rng.randn(50, 100) * .15, rng.randn(50) * .1,
@@ -277,8 +287,9 @@ def test_vnet_detector_classes(mvn):
     # batch above the small-batch threshold goes through the fused kernel: same bits
     reps = 2048 // y.shape[0] + 1
     big = det(cu(np.tile(y, (reps, 1))), 'val').cpu().numpy()
-    assert np.array_equal(big[:y.shape[0]], out.cpu().numpy())
-    assert np.array_equal(big[-y.shape[0]:], out.cpu().numpy())
+    assert np.array_equal(big[:y.shape[0]], big[-y.shape[0]:])          # replicas decode identically
+    # fused (tensor-core layer 2) vs priors-kernel + ACS-kernel: priors agree to ~1e-7, so only a near-tie can differ
+    assert (big[:y.shape[0]] != out.cpu().numpy()).any(axis=1).sum() <= 1
     pri = det(cu(y), 'train')
     assert pri.shape == y.shape + (16,)
     assert rel_to_rowmax(pri.detach().cpu().numpy(), g['trained_priors']) < PRIOR_RTOL
@@ -304,7 +315,7 @@ def test_error_rates_golden(mvn, k):
     assert np.array_equal(idx.cpu().numpy(), g[f'idx_{k}'])
 
 
-def test_error_counts_pilots_and_fused_counters(mvn):
+def test_error_counts_pilots_and_fused_counters(mvn, fused_impl):
     g = load_golden('vnet')
     w, y = _w(g, 'trained_w'), g['y']
     rng = np.random.RandomState(3)
@@ -368,7 +379,7 @@ def test_host_pipeline_matches_device_path(mvn):
 
 
 # ------------------------------------------------------------------------------- full size
-def test_full_size_properties(mvn):
+def test_full_size_properties(mvn, fused_impl):
     """BASELINE.json sizes (1M frames x 120): frames are independent, so a batch built from 4096
     distinct frames repeated in shuffled order must decode every copy exactly like the oracle decodes
     the distinct frame — for the VA (bit-exact) and for the fused ViterbiNet (own-priors protocol)."""
@@ -399,7 +410,7 @@ def test_full_size_properties(mvn):
 
 
 # ------------------------------------------------------------------------------- shared state / sweeps
-def test_constant_slots_are_safe_across_streams(mvn):
+def test_constant_slots_are_safe_across_streams(mvn, fused_impl):
     """The fused kernel keeps its weights in two constant-bank slots; interleaved calls with DIFFERENT
     weights on different streams must not see each other's weights."""
     rng = np.random.RandomState(5)

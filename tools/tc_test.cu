@@ -1,0 +1,183 @@
+// Stand-alone bring-up test for the tcgen05 path of MLP layer 2:
+//   D[128 x 64] (fp32, TMEM) = sum over 6 bf16 piece products of A[128 x 112] (TMEM, written with tcgen05.st)
+//   times B[64 x 112]^T (shared memory, K-major canonical no-swizzle layout).
+// A = h1 (fp32) split exactly into three bf16 pieces a1+a2+a3; B = W2 likewise; the products
+// a1b1, a1b2, a2b1, a1b3, a2b2, a3b1 reproduce the fp32 product to ~2^-24.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tc_test tc_test.cu ; run on a B200.
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+#include <cmath>
+#include <vector>
+#include <cuda_runtime.h>
+
+constexpr int M = 128, N = 64, K = 112, KREAL = 100, NREAL = 50;
+constexpr int KSTEPS = K / 16;             // UMMA_K = 16 for bf16
+constexpr int A_COLS = K / 2;              // 32-bit TMEM columns per A piece
+constexpr int TMEM_COLS = 256;             // D (64) + 3 A pieces (168) -> power of two
+constexpr uint32_t LBO = (N / 8) * 128;    // bytes between the two 16-byte K chunks of one MMA (k-chunk stride)
+constexpr uint32_t SBO = 128;              // bytes between 8-row groups along N
+constexpr int B_PIECE_BYTES = (K / 8) * (N / 8) * 128;   // k-chunks x n-groups x 128 B core matrices
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// exact 3-way split by truncation: x = p1 + p2 + p3, each piece has <= 8 significant bits (bf16-representable)
+__device__ __forceinline__ void split3(float x, uint32_t &p1, uint32_t &p2, uint32_t &p3) {
+    const uint32_t b1 = __float_as_uint(x) & 0xffff0000u;
+    const float r1 = x - __uint_as_float(b1);
+    const uint32_t b2 = __float_as_uint(r1) & 0xffff0000u;
+    const float r2 = r1 - __uint_as_float(b2);
+    p1 = b1 >> 16;
+    p2 = b2 >> 16;
+    p3 = __float_as_uint(r2) >> 16;   // r2 has <= 8 significant bits: exact
+}
+
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= uint64_t((saddr >> 4) & 0x3fff);
+    d |= uint64_t((LBO >> 4) & 0x3fff) << 16;
+    d |= uint64_t((SBO >> 4) & 0x3fff) << 32;
+    d |= uint64_t(1) << 46;   // descriptor version for sm_100
+    return d;                 // layout_type 0 = SWIZZLE_NONE, base_offset 0
+}
+
+__global__ void __launch_bounds__(128, 1) tc_kernel(const float *A, const float *W, float *D, int pack_order, int *status) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(8) uint64_t bar;
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    // ---- B pieces -> shared memory, canonical K-major no-swizzle: [kchunk][ngroup][row8][8 bf16]
+    for (int idx = tid; idx < N * K; idx += blockDim.x) {
+        const int n = idx / K, k = idx % K;
+        const float w = (n < NREAL && k < KREAL) ? W[n * KREAL + k] : 0.f;
+        uint32_t p[3];
+        split3(w, p[0], p[1], p[2]);
+        const int off = (k / 8) * (N / 8) * 128 + (n / 8) * 128 + (n % 8) * 16 + (k % 8) * 2;
+        for (int q = 0; q < 3; q++) *reinterpret_cast<uint16_t *>(smem + q * B_PIECE_BYTES + off) = uint16_t(p[q]);
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    // make the generic-proxy smem writes visible to the tensor core (async proxy)
+    asm volatile("fence.proxy.async.shared::cta;");
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t lane_base = uint32_t(warp * 32) << 16;
+    const uint32_t tD = tmem, tA = tmem + 64;
+
+    // ---- A row of this thread -> three bf16 piece rows in TMEM (columns = K/2 packed pairs)
+    for (int c0 = 0; c0 < A_COLS; c0 += 8) {
+        uint32_t v[3][8];
+        for (int c = 0; c < 8; c++) {
+            const int k0 = 2 * (c0 + c);
+            const float x0 = k0 < KREAL ? A[tid * KREAL + k0] : 0.f;
+            const float x1 = k0 + 1 < KREAL ? A[tid * KREAL + k0 + 1] : 0.f;
+            uint32_t a[3], b[3];
+            split3(x0, a[0], a[1], a[2]);
+            split3(x1, b[0], b[1], b[2]);
+            for (int q = 0; q < 3; q++) v[q][c] = pack_order == 0 ? (a[q] | (b[q] << 16)) : (b[q] | (a[q] << 16));
+        }
+        for (int q = 0; q < 3; q++) {
+            const uint32_t addr = tA + q * A_COLS + c0 + lane_base;
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(addr),
+                         "r"(v[q][0]), "r"(v[q][1]), "r"(v[q][2]), "r"(v[q][3]), "r"(v[q][4]), "r"(v[q][5]), "r"(v[q][6]), "r"(v[q][7]));
+        }
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;");
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+
+    // ---- one thread issues the 6 x 7 MMAs and commits to the mbarrier
+    if (tid == 0) {
+        // idesc: D=F32 (1<<4), A=BF16 (1<<7), B=BF16 (1<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+        const int pa[6] = {0, 0, 1, 0, 1, 2}, pb[6] = {0, 1, 0, 2, 1, 0};
+        uint32_t accumulate = 0;
+        for (int t = 5; t >= 0; t--) {   // smallest terms first
+            for (int j = 0; j < KSTEPS; j++) {
+                const uint32_t a_addr = tA + pa[t] * A_COLS + j * 8;
+                const uint64_t b_desc = make_b_desc(smem_u32(smem + pb[t] * B_PIECE_BYTES) + uint32_t(2 * j) * LBO);
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tD),
+                    "r"(a_addr), "l"(b_desc), "r"(idesc), "r"(accumulate));
+                accumulate = 1;
+            }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)));
+    }
+    // ---- everyone waits for the MMAs, then reads its D row
+    {
+        uint32_t done = 0;
+        int spins = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                : "=r"(done)
+                : "r"(smem_u32(&bar)), "r"(0));
+            if (++spins > (1 << 22)) {
+                if (tid == 0) *status = 1;
+                break;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    for (int c0 = 0; c0 < N; c0 += 16) {
+        uint32_t r[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(tD + c0 + lane_base));
+        asm volatile("tcgen05.wait::ld.sync.aligned;");
+        for (int c = 0; c < 16; c++) D[tid * N + c0 + c] = __uint_as_float(r[c]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
+}
+
+int main() {
+    std::vector<float> A(M * KREAL), W(NREAL * KREAL), D(M * N);
+    srand(1);
+    for (auto &x : A) x = rand() / float(RAND_MAX);                       // sigmoid outputs in (0,1)
+    for (auto &x : W) x = (rand() / float(RAND_MAX) - 0.5f) * 0.4f;
+    float *dA, *dW, *dD;
+    int *dS;
+    cudaMalloc(&dA, A.size() * 4); cudaMalloc(&dW, W.size() * 4); cudaMalloc(&dD, D.size() * 4); cudaMalloc(&dS, 4);
+    cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dW, W.data(), W.size() * 4, cudaMemcpyHostToDevice);
+    const int smem = 3 * B_PIECE_BYTES;
+    cudaFuncSetAttribute(tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    for (int order = 0; order < 2; order++) {
+        cudaMemset(dD, 0, D.size() * 4);
+        cudaMemset(dS, 0, 4);
+        tc_kernel<<<1, 128, smem>>>(dA, dW, dD, order, dS);
+        cudaError_t e = cudaDeviceSynchronize();
+        int st = 0;
+        cudaMemcpy(&st, dS, 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
+        double max_err = 0, max_ref = 0, max_pad = 0;
+        for (int m = 0; m < M; m++)
+            for (int n = 0; n < N; n++) {
+                double ref = 0;
+                if (n < NREAL) for (int k = 0; k < KREAL; k++) ref += double(A[m * KREAL + k]) * double(W[n * KREAL + k]);
+                const double err = fabs(D[m * N + n] - ref);
+                if (n < NREAL) { if (err > max_err) max_err = err; if (fabs(ref) > max_ref) max_ref = fabs(ref); }
+                else if (err > max_pad) max_pad = err;
+            }
+        printf("pack_order=%d: cuda=%s timeout=%d max|err|=%.3e (max|ref|=%.3f, rel %.3e) pad-col max=%.3e  D[0][0..3]=%g %g %g %g\n",
+               order, cudaGetErrorString(e), st, max_err, max_ref, max_err / max_ref, max_pad, D[0], D[1], D[2], D[3]);
+        if (e != cudaSuccess) break;
+    }
+    return 0;
+}

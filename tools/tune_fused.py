@@ -18,15 +18,21 @@ bits, y = bench.synth_frames(torch, dev, frames, 10, 1)
 lib = _lib.load()
 lib.mvn_debug_set_variant.restype = ctypes.c_int
 lib.mvn_debug_set_variant.argtypes = [ctypes.c_int]
-names = {0: 'const M2 384 u10 (default)', 1: 'smem M2 256 u10', 2: 'const M2 320 u10'}
+names = {4: 'fma const M2 384 u10', 1: 'fma smem M2 256 u10', 2: 'fma const M2 320 u10', 3: 'tcgen05 bf16x6 layer 2 (default)'}
 ref = None
-for v in sorted(names):
+for v in (4, 1, 2, 3):
     lib.mvn_debug_set_variant(v)
     out = mvn.ops.vnet_decode(y, w)
     torch.cuda.synchronize()
     if ref is None:
         ref = out
     same = bool(torch.equal(out, ref))
+    nbad = int((out != ref).any(dim=1).sum())
+    sub = y[:4096].contiguous()
+    _, pri = mvn.ops.vnet_decode(sub, w, return_priors=True)
+    if v == 4:
+        pri_ref = pri
+    rel = float(((pri - pri_ref).abs() / pri_ref.abs().amax(dim=-1, keepdim=True)).max())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(3):
@@ -36,5 +42,7 @@ for v in sorted(names):
     ms = e0.elapsed_time(e1) / 3
     rate = frames * bench.T / ms / 1e6
     print(f'variant {v} [{names[v]:26s}] {ms:8.3f} ms  {rate:7.3f} Gsym/s  {rate * bench.FLOP_PER_SYMBOL / 1e3:6.2f} TFLOP/s  '
-          f'bits_equal_to_v0={same}', flush=True)
+          f'bits_equal_to_fma={same} frames_differing={nbad} priors_rel_vs_fma={rel:.2e}', flush=True)
 lib.mvn_debug_set_variant(0)
+lib.mvn_debug_tc_timeout.restype = ctypes.c_int
+print('tc timeout flag:', lib.mvn_debug_tc_timeout())
