@@ -306,12 +306,11 @@ static int launch_tc(VnetParams p, cudaStream_t st) {
     auto kern = vnet_decode_tc_kernel<L>;
     MVN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     p.n_warp_tiles = (p.B + 31) / 32;
-    const int warps = tc::kThreads / 32;
-    const int64_t need = (p.n_warp_tiles + warps - 1) / warps;
+    const int64_t need = (p.n_warp_tiles + 3) / 4;
     const int grid = int(std::min<int64_t>(need, sm_count()));
     void *flag = nullptr;
     MVN_CUDA(cudaGetSymbolAddress(&flag, g_tc_timeout));
-    kern<<<grid, tc::kThreads, smem, st>>>(p, static_cast<int *>(flag));
+    kern<<<grid, tc::kThreadsTc, smem, st>>>(p, static_cast<int *>(flag));
     note_launch();
     MVN_CUDA(cudaGetLastError());
     return MVN_OK;
@@ -349,7 +348,7 @@ static int launch_fused(const VnetParams &p, cudaStream_t st) {
 
 // frames decoded by one full wave of CTAs (host pipeline chunk sizing)
 int vnet_frames_per_wave(int L) {
-    const int per_cta = L <= 3 ? 448 * 2 : L == 4 ? 256 : L == 5 ? 384 * 2 : L <= 7 ? 128 * 2 : 128;
+    const int per_cta = L <= 3 ? 448 * 2 : L == 4 ? 128 : L == 5 ? 384 * 2 : L <= 7 ? 128 * 2 : 128;
     return per_cta * sm_count();
 }
 

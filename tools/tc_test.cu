@@ -41,7 +41,7 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t saddr) {
     return d;                 // layout_type 0 = SWIZZLE_NONE, base_offset 0
 }
 
-__global__ void __launch_bounds__(128, 1) tc_kernel(const float *A, const float *W, float *D, int pack_order, int *status) {
+__global__ void __launch_bounds__(128, 1) tc_kernel(const float *A, const float *W, float *D, int pack_order, int *status, long long *timing) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(8) uint64_t bar;
@@ -115,8 +115,37 @@ __global__ void __launch_bounds__(128, 1) tc_kernel(const float *A, const float 
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)));
     }
+    // ---- timing: REPS batches of 42 MMAs, each committed and waited for by the issuing thread
+    if (tid == 0 && timing) {
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+        uint32_t parity = 0;
+        // drain the correctness batch first
+        { uint32_t done = 0; while (!done) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(smem_u32(&bar)), "r"(parity)); parity ^= 1; }
+        long long t_issue = 0, t_total = 0;
+        const int REPS = 200;
+        for (int rep = 0; rep < REPS; rep++) {
+            const long long c0 = clock64();
+            for (int t = 0; t < 6; t++)
+                for (int j = 0; j < KSTEPS; j++) {
+                    const uint32_t a_addr = tA + (t % 3) * A_COLS + j * 8;
+                    const uint64_t b_desc = make_b_desc(smem_u32(smem + (t % 3) * B_PIECE_BYTES) + uint32_t(2 * j) * LBO);
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tD), "r"(a_addr), "l"(b_desc), "r"(idesc), "r"(1));
+                }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)));
+            const long long c1 = clock64();
+            { uint32_t done = 0; while (!done) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(smem_u32(&bar)), "r"(parity)); parity ^= 1; }
+            const long long c2 = clock64();
+            t_issue += c1 - c0;
+            t_total += c2 - c0;
+        }
+        timing[0] = t_issue / REPS;
+        timing[1] = t_total / REPS;
+        // restore the parity expected by the readers below: they wait for parity 0 of the FIRST phase, already complete
+    }
+    __syncthreads();
     // ---- everyone waits for the MMAs, then reads its D row
-    {
+    if (!timing) {
         uint32_t done = 0;
         int spins = 0;
         while (!done) {
@@ -161,7 +190,7 @@ int main() {
     for (int order = 0; order < 2; order++) {
         cudaMemset(dD, 0, D.size() * 4);
         cudaMemset(dS, 0, 4);
-        tc_kernel<<<1, 128, smem>>>(dA, dW, dD, order, dS);
+        tc_kernel<<<1, 128, smem>>>(dA, dW, dD, order, dS, nullptr);
         cudaError_t e = cudaDeviceSynchronize();
         int st = 0;
         cudaMemcpy(&st, dS, 4, cudaMemcpyDeviceToHost);
@@ -179,5 +208,12 @@ int main() {
                order, cudaGetErrorString(e), st, max_err, max_ref, max_err / max_ref, max_pad, D[0], D[1], D[2], D[3]);
         if (e != cudaSuccess) break;
     }
+    long long *dT, hT[2];
+    cudaMalloc(&dT, 16);
+    tc_kernel<<<1, 128, smem>>>(dA, dW, dD, 0, dS, dT);
+    cudaError_t e2 = cudaDeviceSynchronize();
+    cudaMemcpy(hT, dT, 16, cudaMemcpyDeviceToHost);
+    printf("timing (%s): 42 MMAs M=128 N=64 K=16 bf16, A from TMEM: issue %lld cycles, issue->complete %lld cycles per batch (floor model 42*32 = 1344)\n",
+           cudaGetErrorString(e2), hT[0], hT[1]);
     return 0;
 }
