@@ -1,6 +1,6 @@
 // End-to-end entry points with HOST buffers: a double-buffered chunk pipeline
 //   H2D(y chunk i+1)  ||  fused decode(chunk i)  ||  D2H(bits chunk i-1)
-// on two private streams, so PCIe copies overlap the kernel.  This is the call bench.py times
+// on three private streams, so PCIe copies overlap the kernel.  This is the call bench.py times
 // for `e2e`; it is what a caller holding numpy/CPU tensors (the reference's dataset output,
 // channel_dataset.py:97-104) would use.
 #include <algorithm>
@@ -15,9 +15,10 @@ struct mvn_ctx {
     int T_max = 0;
     int L = 0;
     int S = 0;
-    cudaStream_t st[2] = {nullptr, nullptr};
-    float *d_y[2] = {nullptr, nullptr};
-    void *d_out[2] = {nullptr, nullptr};
+    static constexpr int kSlots = 3;   // H2D of chunk i+1, kernel of chunk i and D2H of chunk i-1 in flight together
+    cudaStream_t st[kSlots] = {nullptr, nullptr, nullptr};
+    float *d_y[kSlots] = {nullptr, nullptr, nullptr};
+    void *d_out[kSlots] = {nullptr, nullptr, nullptr};
     float *d_w = nullptr;   // packed w1,b1,w2,b2,w3,b3
     float *d_sp = nullptr;  // state priors table (VA), up to sp_cap floats
     int64_t sp_cap = 0;
@@ -52,7 +53,7 @@ extern "C" int mvn_ctx_create(mvn_ctx **out, int device, int64_t chunk_frames, i
     c->L = L;
     c->S = 1 << L;
     cudaError_t e = cudaSetDevice(device);
-    for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+    for (int i = 0; i < mvn_ctx::kSlots && e == cudaSuccess; i++) {
         e = cudaStreamCreateWithFlags(&c->st[i], cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaMalloc(&c->d_y[i], size_t(chunk_frames) * T_max * sizeof(float));
         if (e == cudaSuccess) e = cudaMalloc(&c->d_out[i], size_t(chunk_frames) * T_max * sizeof(float));
@@ -69,7 +70,7 @@ extern "C" int mvn_ctx_create(mvn_ctx **out, int device, int64_t chunk_frames, i
 extern "C" void mvn_ctx_destroy(mvn_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < mvn_ctx::kSlots; i++) {
         if (c->st[i]) cudaStreamSynchronize(c->st[i]);
         if (c->d_y[i]) cudaFree(c->d_y[i]);
         if (c->d_out[i]) cudaFree(c->d_out[i]);
@@ -110,7 +111,7 @@ static int run_pipeline(mvn_ctx *c, const float *y_host, int64_t B, int T, int o
     const int n_words = (T + 31) / 32;
     const size_t out_row = out_format == MVN_OUT_F32 ? size_t(T) * sizeof(float) : size_t(n_words) * sizeof(uint32_t);
     int slot = 0;
-    for (int64_t b0 = 0; b0 < B; b0 += c->chunk, slot ^= 1) {
+    for (int64_t b0 = 0; b0 < B; b0 += c->chunk, slot = (slot + 1) % mvn_ctx::kSlots) {
         const int64_t nb = std::min<int64_t>(c->chunk, B - b0);
         cudaStream_t st = c->st[slot];
         MVN_CUDA(cudaMemcpyAsync(c->d_y[slot], y_host + b0 * T, size_t(nb) * T * sizeof(float), cudaMemcpyHostToDevice, st));
@@ -119,8 +120,7 @@ static int run_pipeline(mvn_ctx *c, const float *y_host, int64_t B, int T, int o
         MVN_CUDA(cudaMemcpyAsync(static_cast<char *>(decoded_host) + size_t(b0) * out_row, c->d_out[slot],
                                  size_t(nb) * out_row, cudaMemcpyDeviceToHost, st));
     }
-    MVN_CUDA(cudaStreamSynchronize(c->st[0]));
-    MVN_CUDA(cudaStreamSynchronize(c->st[1]));
+    for (int i = 0; i < mvn_ctx::kSlots; i++) MVN_CUDA(cudaStreamSynchronize(c->st[i]));
     return MVN_OK;
 }
 

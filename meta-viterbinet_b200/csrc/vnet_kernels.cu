@@ -298,6 +298,9 @@ static int launch_variant(VnetParams p, cudaStream_t st) {
 }
 
 __device__ int g_tc_timeout = 0;
+#ifdef MVN_TC_TRACE
+__device__ long long g_tc_trace[64 * 16];
+#endif
 
 // tcgen05 variant (memory_length <= 4): every CTA stages its own weights (W2/b2 as bf16 pieces, the rest fp32).
 template <int L>
@@ -310,7 +313,11 @@ static int launch_tc(VnetParams p, cudaStream_t st) {
     const int grid = int(std::min<int64_t>(need, sm_count()));
     void *flag = nullptr;
     MVN_CUDA(cudaGetSymbolAddress(&flag, g_tc_timeout));
-    kern<<<grid, tc::kThreadsTc, smem, st>>>(p, static_cast<int *>(flag));
+    void *trace = nullptr;
+#ifdef MVN_TC_TRACE
+    MVN_CUDA(cudaGetSymbolAddress(&trace, g_tc_trace));
+#endif
+    kern<<<grid, tc::kThreadsTc, smem, st>>>(p, static_cast<int *>(flag), static_cast<long long *>(trace));
     note_launch();
     MVN_CUDA(cudaGetLastError());
     return MVN_OK;
@@ -447,3 +454,9 @@ extern "C" int mvn_debug_tc_timeout(void) {
     cudaMemcpyFromSymbol(&v, mvn::g_tc_timeout, sizeof(int));
     return v;
 }
+
+#ifdef MVN_TC_TRACE
+extern "C" int mvn_debug_tc_trace(long long *host_out) {
+    return int(cudaMemcpyFromSymbol(host_out, mvn::g_tc_trace, sizeof(long long) * 64 * 16));
+}
+#endif

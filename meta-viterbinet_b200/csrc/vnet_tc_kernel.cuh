@@ -2,48 +2,62 @@
 // ([symbols,100] x [100,50], 85 % of the flops) runs on the 5th-generation tensor cores, everything
 // else (sigmoid, ReLU, layer 3, ACS, decision) stays on the CUDA cores of the same CTA.
 //
-// fp32 parity on bf16 tensor cores.  h1 and W2 are each split EXACTLY into three bf16 pieces
-// (x = p1 + p2 + p3, 8 significant bits each, by mantissa truncation), and
-//     h1 . w  =  p1q1 + p1q2 + p2q1 + p1q3 + p2q2 + p3q1  + O(2^-24 |h1||w|)
-// is accumulated in fp32 in TMEM by six chains of kind::f16 MMAs (bf16 products are exact in fp32).
-// Measured against fp64 (tools/tc_test.cu): 2e-7 of the row maximum, the same class as the FMA path.
+// fp32 parity on fp16 tensor cores.  Each operand is split into two fp16 pieces with a scaled remainder,
+//     x = hi + lo / 2048,   hi = fp16(x),   lo = fp16((x - hi) * 2048)      (x - hi is exact in fp32),
+// and   h1 . w = hi_h hi_w + (hi_h lo_w + lo_h hi_w) / 2048 + O(2^-22 |h1||w|)   is accumulated in fp32 by
+// two accumulators in TMEM: D_main (one chain of kind::f16 MMAs) and D_corr (two chains); fp16 products are
+// exact in fp32 and the 2^11 scaling keeps the remainders normal.  On the reference's fixtures the priors are
+// 2.4e-7 of the row maximum away from fp64 — closer than a plain fp32 dot product (4.4e-7), see DESIGN.md §5.1.
+// (A first version used an exact three-way bf16 split with six chains: same accuracy, twice the tensor work.)
 // The bias b2 rides along as column k=100 of B against a constant-1 column of A.
 //
-// Data flow per trellis stage for the 128 frames of a CTA tile (one frame = one TMEM lane):
-//   producers  : 100 sigmoids -> 3-way split -> tcgen05.st   A pieces [128 x 112] bf16 in TMEM (168 columns)
-//   MMA warp   : 6 x 7 tcgen05.mma.kind::f16 (M=128, N=64, K=16), A from TMEM, B (W2 pieces) from shared memory
-//                in the canonical K-major no-swizzle layout, D [128 x 64] fp32 in TMEM; tcgen05.commit -> mbarrier
-//   consumers  : tcgen05.ld of the frame's D row -> ReLU -> layer 3 (FFMA2) -> ACS on the frame's 8 private
-//                path metrics -> decision bit, outputs, BER
-// TMEM: a two-slot ring of (64 D + 168 A) columns -> the whole 512-column allocation, one CTA per SM.
+// Warp-specialised pipeline over a two-slot TMEM ring; one frame = one TMEM lane, 128 frames per CTA tile:
+//   8 producer warps : y -> 100 sigmoids -> fp16 hi/lo split -> tcgen05.st  A_hi, A_lo [128 x 112] (2 x 56 columns)
+//                      (warps w and w+4 serve the same 32 frames and split the hidden units)
+//   1 MMA warp       : per stage 3 x 7 tcgen05.mma.kind::f16 (M=128, N=64, K=16), A from TMEM, B (W2 pieces) from
+//                      shared memory in the canonical K-major no-swizzle layout; tcgen05.commit -> d_full[slot]
+//   4 consumer warps : tcgen05.ld D_main/D_corr -> combine -> ReLU -> the same hi/lo split -> tcgen05.st as the A
+//                      operand of LAYER 3, which also runs on the tensor core (3 x 4 MMAs, N=16, W3 pieces and b3 in
+//                      shared memory, issued by one consumer thread); tcgen05.ld of the 16 priors -> ACS on the
+//                      frame's 8 private path metrics, decision bit, outputs, BER.  No weight traffic on the LSU.
+// The sigmoid/split/MMA work of later stages does not depend on the ACS result of earlier ones (only the
+// decision chain is sequential), which is what lets producers and the tensor core run ahead.
+// TMEM: 2 x (64 + 64 + 56 + 56) columns of the 512-column allocation, one CTA per SM; layer 3 reuses the slot's
+// A columns for h2 and its D columns for the priors once layer 2's results have been read.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "vnet_mlp.cuh"
 
 namespace mvn {
 
+#ifndef MVN_NR_ALL
+#define MVN_NR_ALL 0
+#endif
 namespace tc {
 constexpr int kM = 128, kN = 64, kK = 112;    // MMA tile: frames x padded outputs x padded hidden units (+ bias column)
-constexpr int kKSteps = kK / 16;              // UMMA_K = 16 for bf16
-constexpr int kACols = kK / 2;                // 32-bit TMEM columns per A piece (two bf16 per column)
-constexpr int kGroupCols = 256;               // D (64) + 3 x 56 A columns, rounded to the allocation granularity
+constexpr int kKSteps = kK / 16;              // UMMA_K = 16 for fp16
+constexpr int kACols = kK / 2;                // 32-bit TMEM columns per A piece (two fp16 per column)
+constexpr int kSlotCols = 256;                // slot stride; 240 used: D_main | D_corr | A_hi | A_lo
+constexpr int oDm = 0, oDc = kN, oAh = 2 * kN, oAl = 2 * kN + kACols;
+constexpr float kScale = 2048.f, kInvScale = 1.f / 2048.f;
 constexpr uint32_t kLBO = (kN / 8) * 128;     // bytes between consecutive 16-byte K chunks (k-chunk stride)
 constexpr uint32_t kSBO = 128;                // bytes between 8-row groups along N
 constexpr int kBPieceBytes = (kK / 8) * (kN / 8) * 128;
+constexpr int kProdWarps = 8, kConsWarps = 4, kThreadsTc = 32 * (kProdWarps + kConsWarps + 1);  // + one MMA-issue warp
+// layer 3 on the tensor core as well: D2[128 x 16] = h2[128 x 64] W3^T, K2 = 50 hidden units + bias column, padded
+constexpr int kN2 = 16, kK2 = 64, kK2Steps = kK2 / 16, kA2Cols = kK2 / 2;
+constexpr uint32_t kLBO2 = (kN2 / 8) * 128;
+constexpr int kB2PieceBytes = (kK2 / 8) * (kN2 / 8) * 128;
 
-__device__ __forceinline__ uint32_t hi16(float x) { return __float_as_uint(x) & 0xffff0000u; }
-
-// exact split x = p1 + p2 + p3 (each representable in bf16); returns the three bf16 bit patterns << 16
-__device__ __forceinline__ void split3(float x, uint32_t &b1, uint32_t &b2, uint32_t &b3) {
-    b1 = hi16(x);
-    const float r1 = x - __uint_as_float(b1);
-    b2 = hi16(r1);
-    b3 = __float_as_uint(r1 - __uint_as_float(b2));  // <= 8 significant bits left: exact in bf16
+__device__ __forceinline__ void split_f16(float x, uint16_t &hi, uint16_t &lo) {
+    const __half h = __float2half_rn(x);
+    const __half l = __float2half_rn((x - __half2float(h)) * kScale);
+    hi = __half_as_ushort(h);
+    lo = __half_as_ushort(l);
 }
-// (lo, hi) bf16 pair from two fp32 patterns whose low 16 bits are zero / to be dropped
-__device__ __forceinline__ uint32_t pack_hi16(uint32_t lo, uint32_t hi) { return __byte_perm(lo, hi, 0x7632); }
-
-__device__ __forceinline__ uint64_t b_desc(uint32_t saddr) {
-    return uint64_t((saddr >> 4) & 0x3fff) | (uint64_t((kLBO >> 4) & 0x3fff) << 16) |
+__device__ __forceinline__ uint64_t b_desc(uint32_t saddr, uint32_t lbo = kLBO) {
+    return uint64_t((saddr >> 4) & 0x3fff) | (uint64_t((lbo >> 4) & 0x3fff) << 16) |
            (uint64_t((kSBO >> 4) & 0x3fff) << 32) | (uint64_t(1) << 46);  // version 1, SWIZZLE_NONE
 }
 __device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -72,19 +86,6 @@ __device__ __forceinline__ void tmem_ld2(uint32_t addr, float *r) {
     r[0] = __uint_as_float(u0);
     r[1] = __uint_as_float(u1);
 }
-}  // namespace tc
-
-// ---------------------------------------------------------------------------------------------
-// Warp-specialised pipeline.  The sigmoid/split/store work of stage t+1 does not depend on the ACS
-// result of stage t (only the decision chain is sequential), so the CTA is split into
-//   8 producer warps : y -> 100 sigmoids -> bf16x3 split -> tcgen05.st into A[slot]; one of them issues the MMAs
-//   4 consumer warps : tcgen05.ld D[slot] -> ReLU -> layer 3 -> ACS -> decision, outputs, BER
-// over a two-slot TMEM ring (2 x (64 D + 168 A) columns).  Producer warps w and w+4 serve the same 32
-// frames (TMEM lane quadrant w) and split the hidden units between them; consumer warp 8+w owns those
-// frames' path metrics.  mbarriers: d_full[slot] (tcgen05.commit) and slot_free[slot] (128 consumer arrivals).
-// ---------------------------------------------------------------------------------------------
-namespace tc {
-constexpr int kProdWarps = 8, kConsWarps = 4, kThreadsTc = 32 * (kProdWarps + kConsWarps + 1);  // + one MMA-issue warp
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int *timeout_flag) {
     uint32_t done = 0;
     int spins = 0;
@@ -100,84 +101,135 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int *ti
         }
     }
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 // ---- producer math on fp32x2 pairs of hidden units (k, k+1) --------------------------------------
 // staged pair table: sP[k/2] = (w1'[k], w1'[k+1], b1'[k], b1'[k+1]) with w1' = -log2(e) w1 (one LDS.128)
-__device__ __forceinline__ u64 sub2(u64 a, u64 b) {  // a - b on both halves: b * (-1) + a, the product is exact
-    u64 d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(b), "l"(0xbf800000bf800000ull), "l"(a));
-    return d;
-}
-__device__ __forceinline__ u64 hi16x2(u64 v) { return v & 0xffff0000ffff0000ull; }
-__device__ __forceinline__ uint32_t pack_hi16x2(u64 v) { return __byte_perm(uint32_t(v), uint32_t(v >> 32), 0x7632); }
-
-// (h_k, h_{k+1}) -> the three packed bf16 pair words
-__device__ __forceinline__ void split3x2(u64 h, uint32_t &w1, uint32_t &w2, uint32_t &w3) {
-    const u64 r1 = sub2(h, hi16x2(h));
-    const u64 r2 = sub2(r1, hi16x2(r1));
-    w1 = pack_hi16x2(h);
-    w2 = pack_hi16x2(r1);
-    w3 = pack_hi16x2(r2);  // <= 8 significant bits left in each half: exact
-}
+// The producers are bound by the XU (MUFU) pipe: 16 lanes per clock per SM, and EX2 + RCP for 100 hidden units is
+// 200 MUFU per symbol (pipeline trace: profiles/r01_tc_pipeline_trace_v4.txt).  NR = true computes the reciprocal on
+// the idle FMA pipe instead: bit-trick seed (|err| < 12.5 %) and three Newton steps r += r (1 - d r) on packed
+// pairs (6e-8 after the third); the callers alternate the two forms to balance XU and issue slots.
+template <bool NR>
 __device__ __forceinline__ u64 sigmoid2(uint32_t sP_addr, int pair, u64 yy) {
     u64 w, b;
     lds128(sP_addr + 16 * pair, w, b);
     float x0, x1;
     unpack2(fma2(yy, w, b), x0, x1);
-    float d0, d1;
-    unpack2(add2(pack2(ex2_approx(x0), ex2_approx(x1)), 0x3f8000003f800000ull), d0, d1);
-    return pack2(rcp_approx(d0), rcp_approx(d1));
+    if (!NR) {
+        float d0, d1;
+        unpack2(add2(pack2(ex2_approx(x0), ex2_approx(x1)), 0x3f8000003f800000ull), d0, d1);
+        return pack2(rcp_approx(d0), rcp_approx(d1));
+    } else {
+        // clamp the exponent so that d = 1 + 2^x stays finite (sigmoid < 2^-80 is 0 to every later digit)
+        const u64 d = add2(pack2(ex2_approx(fminf(x0, 80.f)), ex2_approx(fminf(x1, 80.f))), 0x3f8000003f800000ull);
+        float d0, d1;
+        unpack2(d, d0, d1);
+        u64 r = pack2(__uint_as_float(0x7ef311c7u - __float_as_uint(d0)), __uint_as_float(0x7ef311c7u - __float_as_uint(d1)));
+        const u64 nd = d ^ 0x8000000080000000ull;
+#pragma unroll
+        for (int it = 0; it < 3; it++) r = fma2(r, fma2(nd, r, 0x3f8000003f800000ull), r);
+        return r;
+    }
 }
-// one k-step (16 hidden units = 8 TMEM columns) of this thread's frame: sigmoid -> split -> 3 x tcgen05.st
+// (h_k, h_{k+1}) -> fp16x2 words of the hi pieces and of the scaled remainders (low half = even k)
+__device__ __forceinline__ void split2_f16(u64 h, uint32_t &whi, uint32_t &wlo) {
+    float h0, h1;
+    unpack2(h, h0, h1);
+    const __half2 hi = __floats2half2_rn(h0, h1);
+    const float2 f = __half22float2(hi);
+    // (h - f) * 2048 on both halves: f * (-2048) + h * 2048, every step exact except the final fp16 rounding
+    float r0, r1;
+    unpack2(fma2(pack2(f.x, f.y), 0xc5000000c5000000ull, mul2(h, 0x4500000045000000ull)), r0, r1);
+    const __half2 lo = __floats2half2_rn(r0, r1);
+    whi = *reinterpret_cast<const uint32_t *>(&hi);
+    wlo = *reinterpret_cast<const uint32_t *>(&lo);
+}
+// one k-step (16 hidden units = 8 TMEM columns) of this thread's frame: sigmoid -> split into registers
 template <bool LAST>
-__device__ __forceinline__ void produce_chunk(uint32_t sP_addr, int c0, u64 yy, uint32_t tA_lane) {
-    uint32_t v[3][8];
+__device__ __forceinline__ void compute_chunk(uint32_t sP_addr, int c0, u64 yy, uint32_t (&vh)[8], uint32_t (&vl)[8]) {
 #pragma unroll
     for (int c = 0; c < 8; c++) {
         if (!LAST || c < 2) {
-            split3x2(sigmoid2(sP_addr, 8 * c0 + c, yy), v[0][c], v[1][c], v[2][c]);
-        } else {  // k = 100 is the bias column (1.0 = bf16 0x3F80 in the low half), k > 100 is zero padding
-            v[0][c] = (c == 2) ? 0x00003f80u : 0u;
-            v[1][c] = 0u;
-            v[2][c] = 0u;
+            if (MVN_NR_ALL || (c & 1)) split2_f16(sigmoid2<true>(sP_addr, 8 * c0 + c, yy), vh[c], vl[c]);
+            else split2_f16(sigmoid2<false>(sP_addr, 8 * c0 + c, yy), vh[c], vl[c]);
+        } else {  // k = 100 is the bias column (1.0 = fp16 0x3C00 in the low half), k > 100 is zero padding
+            vh[c] = (c == 2) ? 0x00003c00u : 0u;
+            vl[c] = 0u;
         }
     }
-#pragma unroll
-    for (int i = 0; i < 3; i++) tmem_st8(tA_lane + i * kACols + c0 * 8, v[i]);
 }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+// consumer, step 1: h2 = relu(D_main + D_corr / 2048) of this thread's frame, split into fp16 hi / scaled lo,
+// stored as the A operand of layer 3 (columns 0..31 of the slot's A_hi / A_lo regions, free after the MMAs of
+// layer 2); column k2 = 50 is the constant 1 that multiplies the b3 row of B2.
+__device__ __forceinline__ void h2_to_tmem(uint32_t slot_lane) {
+#pragma unroll
+    for (int c0 = 0; c0 < kK2Steps; c0++) {   // 16 hidden units = 8 columns per step
+        float m[16], c[16];
+        tmem_ld16(slot_lane + oDm + 16 * c0, m);
+        tmem_ld16(slot_lane + oDc + 16 * c0, c);
+        asm volatile("tcgen05.wait::ld.sync.aligned;");
+        uint32_t vh[8], vl[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int k = 16 * c0 + 2 * q;
+            if (k + 1 < kH2) {
+                const float h0 = fmaxf(fmaf(c[2 * q], kInvScale, m[2 * q]), 0.f);
+                const float h1 = fmaxf(fmaf(c[2 * q + 1], kInvScale, m[2 * q + 1]), 0.f);
+                split2_f16(pack2(h0, h1), vh[q], vl[q]);
+            } else {  // k2 = 50: bias column (1.0 in the low half); beyond: zero padding
+                vh[q] = (k == kH2) ? 0x00003c00u : 0u;
+                vl[q] = 0u;
+            }
+        }
+        tmem_st8(slot_lane + oAh + c0 * 8, vh);
+        tmem_st8(slot_lane + oAl + c0 * 8, vl);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;");
 }
 }  // namespace tc
 
+// Optional pipeline trace (debug builds only, -DMVN_TC_TRACE): CTA 0 records clock64() at the key points of the
+// first 64 stages, 16 events per stage, into trace[stage*16 + event].
+#ifdef MVN_TC_TRACE
+#define TC_TRACE(ev, cond)                                                                               \
+    do {                                                                                                 \
+        if (trace && blockIdx.x == 0 && (cond) && n < 64) trace[n * 16 + (ev)] = clock64();                 \
+    } while (0)
+#else
+#define TC_TRACE(ev, cond) do {} while (0)
+#endif
+
 template <int L>
-__global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetParams p, int *timeout_flag) {
+__global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetParams p, int *timeout_flag, long long *trace) {
     static_assert(L <= 4, "tcgen05 variant: register trellis, one layer-3 chunk");
     using D = TrellisDims<L>;
-    using W = VnetSmem<L>;
     constexpr int S = D::S, C = D::C, NW = tc::kProdWarps + tc::kConsWarps;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint32_t tmem_base_s;
-    __shared__ __align__(8) uint64_t d_full[2], slot_free[2], a_full[2];
-    uint8_t *sB = smem_raw;
-    float *tiles = reinterpret_cast<float *>(smem_raw + 3 * tc::kBPieceBytes);  // one 32x32 tile per warp
-    float *sW = tiles + NW * kTileFloats;
+    __shared__ __align__(8) uint64_t d_full[2], slot_free[2], a_full[2], d2_full;
+    constexpr int NT_TILES = tc::kProdWarps + tc::kConsWarps;                    // producers and consumers stage tiles
+    uint8_t *sB = smem_raw;                                                      // W2 pieces: hi | lo
+    float *tiles = reinterpret_cast<float *>(smem_raw + 2 * tc::kBPieceBytes);   // one 32x32 tile per such warp
+    float *sP = tiles + NT_TILES * kTileFloats;                                  // [56][4] pair table for the packed sigmoid
+    uint8_t *sB2 = reinterpret_cast<uint8_t *>(sP + 4 * (tc::kK / 2));           // W3 (+ b3 column) pieces: hi | lo
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, quad = warp & 3;
     const bool producer = warp < tc::kProdWarps;
     const bool mma_warp = warp == NW;
-    float *tile = tiles + warp * kTileFloats;
+    float *tile = tiles + (warp < NT_TILES ? warp : 0) * kTileFloats;
 
+    // ---- W2 (and b2 as column k=100) -> fp16 hi / scaled-lo pieces in the canonical K-major layout
     for (int idx = tid; idx < tc::kN * tc::kK; idx += tc::kThreadsTc) {
         const int n = idx / tc::kK, k = idx % tc::kK;
         float w = 0.f;
         if (n < kH2) w = k < kH1 ? p.w.w2[n * kH1 + k] : (k == kH1 ? p.w.b2[n] : 0.f);
-        uint32_t q[3];
-        tc::split3(w, q[0], q[1], q[2]);
+        uint16_t hi, lo;
+        tc::split_f16(w, hi, lo);
         const int off = (k / 8) * (tc::kN / 8) * 128 + (n / 8) * 128 + (n % 8) * 16 + (k % 8) * 2;
-#pragma unroll
-        for (int i = 0; i < 3; i++) *reinterpret_cast<uint16_t *>(sB + i * tc::kBPieceBytes + off) = uint16_t(q[i] >> 16);
+        *reinterpret_cast<uint16_t *>(sB + off) = hi;
+        *reinterpret_cast<uint16_t *>(sB + tc::kBPieceBytes + off) = lo;
     }
-    stage_weights<L>(sW, p.w, tid, tc::kThreadsTc);
-    float *sP = sW + W::kFloats;  // [56][4] pair table for the producers' packed sigmoid
     for (int i = tid; i < tc::kK / 2; i += tc::kThreadsTc) {
         const float kNegLog2e = -1.4426950408889634f;
         const int k = 2 * i;
@@ -186,6 +238,17 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
         sP[4 * i + 2] = k < kH1 ? p.w.b1[k] * kNegLog2e : 0.f;
         sP[4 * i + 3] = k + 1 < kH1 ? p.w.b1[k + 1] * kNegLog2e : 0.f;
     }
+    // ---- W3 (and b3 as column k2=50) -> fp16 pieces, canonical K-major layout with N2 = 16 rows (states)
+    for (int idx = tid; idx < tc::kN2 * tc::kK2; idx += tc::kThreadsTc) {
+        const int n2 = idx / tc::kK2, k = idx % tc::kK2;
+        float w = 0.f;
+        if (n2 < S) w = k < kH2 ? p.w.w3[n2 * kH2 + k] : (k == kH2 ? p.w.b3[n2] : 0.f);
+        uint16_t hi, lo;
+        tc::split_f16(w, hi, lo);
+        const int off = (k / 8) * (tc::kN2 / 8) * 128 + (n2 / 8) * 128 + (n2 % 8) * 16 + (k % 8) * 2;
+        *reinterpret_cast<uint16_t *>(sB2 + off) = hi;
+        *reinterpret_cast<uint16_t *>(sB2 + tc::kB2PieceBytes + off) = lo;
+    }
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < 2; s++) {
@@ -193,21 +256,23 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&slot_free[s])), "n"(32 * tc::kConsWarps));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&a_full[s])), "n"(32 * tc::kProdWarps));
         }
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&d2_full)));
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_s)), "n"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    asm volatile("fence.proxy.async.shared::cta;");
+    asm volatile("fence.proxy.async.shared::cta;");  // generic-proxy writes of B -> visible to the tensor core
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem = tmem_base_s;
     const uint32_t lane_base = uint32_t(quad * 32) << 16;
-    const uint32_t sB_addr = smem_addr(sB);
-    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(tc::kN >> 3) << 17) | (uint32_t(tc::kM >> 4) << 24);
-    const Wt<kSmem> wt{smem_addr(sW)};
+    const uint32_t sB_addr = smem_addr(sB), sB2_addr = smem_addr(sB2);
+    constexpr uint32_t idesc2 = (1u << 4) | (uint32_t(tc::kN2 >> 3) << 17) | (uint32_t(tc::kM >> 4) << 24);
+    // D=F32, A=B=F16, both K-major, N>>3 at bit 17, M>>4 at bit 24
+    constexpr uint32_t idesc = (1u << 4) | (uint32_t(tc::kN >> 3) << 17) | (uint32_t(tc::kM >> 4) << 24);
     const uint32_t sP_addr = smem_addr(sP);
     const bool vec_in = is_vec_ok(p.y, p.T, p.T);
     const bool vec_out = p.out_format == MVN_OUT_F32 && is_vec_ok(p.decoded, p.T, p.T);
@@ -217,7 +282,6 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
     uint32_t n = 0;                                        // running stage counter: slot = n & 1, use = n >> 1
 
     if (producer) {
-        // hidden units of this producer warp: warps 0-3 take k-steps 0..3, warps 4-7 take k-steps 4..6
         for (int64_t ct = blockIdx.x; ct < n_cta_tiles; ct += gridDim.x) {
             const int64_t row0 = (ct * 4 + quad) * 32;
             for (int t0 = 0; t0 < p.T; t0 += 32) {
@@ -227,23 +291,37 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
 #pragma unroll 1
                 for (int tt = 0; tt < t_end; tt++, n++) {
                     const uint32_t slot = n & 1, use = n >> 1;
-                    const uint32_t tA = tmem + slot * tc::kGroupCols + tc::kN;
+                    const uint32_t slot_lane = tmem + slot * tc::kSlotCols + lane_base;
                     const float yv = tile[lane * kTileLd + tt];
+                    const u64 yy = pack2(yv, yv);
+                    // Compute this stage's pieces into registers BEFORE waiting for the slot: the sigmoid/split work
+                    // then overlaps the MMAs and the consumer of the stage that still owns the slot.
+                    TC_TRACE(0, tid == 0);
+                    constexpr int NCH = 4;                       // k-steps per producer warp (the upper half has 3)
+                    const int c_base = warp < 4 ? 0 : 4;
+                    uint32_t vh[NCH][8], vl[NCH][8];
+                    if (warp < 4) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) tc::compute_chunk<false>(sP_addr, i, yy, vh[i], vl[i]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 2; i++) tc::compute_chunk<false>(sP_addr, 4 + i, yy, vh[i], vl[i]);
+                        tc::compute_chunk<true>(sP_addr, 6, yy, vh[2], vl[2]);
+                    }
+                    TC_TRACE(1, tid == 0);
                     tc::mbar_wait(smem_addr(&slot_free[slot]), (use & 1) ^ 1, timeout_flag);
                     asm volatile("tcgen05.fence::after_thread_sync;");
-                    {
-                        const u64 yy = pack2(yv, yv);
-                        if (warp < 4) {
-#pragma unroll 1
-                            for (int c0 = 0; c0 < 4; c0++) tc::produce_chunk<false>(sP_addr, c0, yy, tA + lane_base);
-                        } else {
-#pragma unroll 1
-                            for (int c0 = 4; c0 < tc::kKSteps - 1; c0++) tc::produce_chunk<false>(sP_addr, c0, yy, tA + lane_base);
-                            tc::produce_chunk<true>(sP_addr, tc::kKSteps - 1, yy, tA + lane_base);
+                    TC_TRACE(2, tid == 0);
+#pragma unroll
+                    for (int i = 0; i < NCH; i++) {
+                        if (warp < 4 || i < 3) {
+                            tc::tmem_st8(slot_lane + tc::oAh + (c_base + i) * 8, vh[i]);
+                            tc::tmem_st8(slot_lane + tc::oAl + (c_base + i) * 8, vl[i]);
                         }
                     }
                     asm volatile("tcgen05.wait::st.sync.aligned;");
                     asm volatile("tcgen05.fence::before_thread_sync;");
+                    TC_TRACE(3, tid == 0);
                     tc::mbar_arrive(smem_addr(&a_full[slot]));  // 256 arrivals release the MMA warp
                     __syncwarp();
                 }
@@ -251,8 +329,7 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
             }
         }
     } else if (mma_warp) {
-        // one warp does nothing but issue: per stage 6 x 7 MMAs (about 2 000 cycles of issue time, which a
-        // producer warp would otherwise spend blocked), then tcgen05.commit -> d_full[slot]
+        // one warp does nothing but issue: per stage 3 x 7 MMAs, then tcgen05.commit -> d_full[slot]
         for (int64_t ct = blockIdx.x; ct < n_cta_tiles; ct += gridDim.x) {
             for (int t0 = 0; t0 < p.T; t0 += 32) {
                 const int t_end = min(32, p.n_stages - t0);
@@ -261,23 +338,24 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
                     const uint32_t slot = n & 1, use = n >> 1;
                     tc::mbar_wait(smem_addr(&a_full[slot]), use & 1, timeout_flag);
                     asm volatile("tcgen05.fence::after_thread_sync;");
+                    TC_TRACE(4, lane == 0);
                     if (lane == 0) {
-                        const uint32_t tD = tmem + slot * tc::kGroupCols, tA = tD + tc::kN;
-                        uint32_t accum = 0;
+                        const uint32_t ts = tmem + slot * tc::kSlotCols;
 #pragma unroll
-                        for (int t = 5; t >= 0; t--) {
-                            const int pa = (t == 2 || t == 4) ? 1 : (t == 5 ? 2 : 0);
-                            const int pb = (t == 1 || t == 4) ? 1 : (t == 3 ? 2 : 0);
+                        for (int j = 0; j < tc::kKSteps; j++)   // D_main = A_hi B_hi
+                            tc::mma_f16_ts(ts + tc::oDm, ts + tc::oAh + j * 8, tc::b_desc(sB_addr + uint32_t(2 * j) * tc::kLBO), idesc,
+                                           j > 0);
 #pragma unroll
-                            for (int j = 0; j < tc::kKSteps; j++) {
-                                tc::mma_f16_ts(tD, tA + pa * tc::kACols + j * 8,
-                                               tc::b_desc(sB_addr + pb * tc::kBPieceBytes + uint32_t(2 * j) * tc::kLBO), idesc, accum);
-                                accum = 1;
-                            }
-                        }
+                        for (int j = 0; j < tc::kKSteps; j++)   // D_corr = A_hi B_lo + A_lo B_hi
+                            tc::mma_f16_ts(ts + tc::oDc, ts + tc::oAh + j * 8,
+                                           tc::b_desc(sB_addr + tc::kBPieceBytes + uint32_t(2 * j) * tc::kLBO), idesc, j > 0);
+#pragma unroll
+                        for (int j = 0; j < tc::kKSteps; j++)
+                            tc::mma_f16_ts(ts + tc::oDc, ts + tc::oAl + j * 8, tc::b_desc(sB_addr + uint32_t(2 * j) * tc::kLBO), idesc, 1);
                         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                             smem_addr(&d_full[slot])));
                     }
+                    TC_TRACE(5, lane == 0);
                     __syncwarp();
                 }
             }
@@ -296,34 +374,58 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
 #pragma unroll 1
                 for (int tt = 0; tt < t_end; tt++, n++) {
                     const uint32_t slot = n & 1, use = n >> 1;
-                    const uint32_t tD = tmem + slot * tc::kGroupCols;
-                    bits |= tr.decide() << tt;
+                    const uint32_t ts = tmem + slot * tc::kSlotCols, slot_lane = ts + lane_base;
+                    TC_TRACE(6, warp == tc::kProdWarps && lane == 0);
                     tc::mbar_wait(smem_addr(&d_full[slot]), use & 1, timeout_flag);
                     asm volatile("tcgen05.fence::after_thread_sync;");
-                    float h2[1][kH2];
-                    {
-                        float d[64];
-                        tc::tmem_ld16(tD + 0 + lane_base, d);
-                        tc::tmem_ld16(tD + 16 + lane_base, d + 16);
-                        tc::tmem_ld16(tD + 32 + lane_base, d + 32);
-                        tc::tmem_ld2(tD + 48 + lane_base, d + 48);
-                        asm volatile("tcgen05.wait::ld.sync.aligned;");
-                        asm volatile("tcgen05.fence::before_thread_sync;");
-                        tc::mbar_arrive(smem_addr(&slot_free[slot]));  // D and A of this slot may be refilled
+                    TC_TRACE(7, warp == tc::kProdWarps && lane == 0);
+                    tc::h2_to_tmem(slot_lane);                       // layer-2 result -> ReLU -> A operand of layer 3
+                    asm volatile("tcgen05.fence::before_thread_sync;");
+                    TC_TRACE(8, warp == tc::kProdWarps && lane == 0);
+                    asm volatile("bar.sync 2, %0;" ::"n"(32 * tc::kConsWarps));
+                    TC_TRACE(9, warp == tc::kProdWarps && lane == 0);
+                    if (warp == tc::kProdWarps && lane == 0) {       // one consumer thread issues layer 3: 3 x 4 MMAs
+                        asm volatile("tcgen05.fence::after_thread_sync;");
 #pragma unroll
-                        for (int o = 0; o < kH2; o++) h2[0][o] = fmaxf(d[o], 0.f);
+                        for (int j = 0; j < tc::kK2Steps; j++)
+                            tc::mma_f16_ts(ts + tc::oDm, ts + tc::oAh + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * tc::kLBO2, tc::kLBO2),
+                                           idesc2, j > 0);
+#pragma unroll
+                        for (int j = 0; j < tc::kK2Steps; j++)
+                            tc::mma_f16_ts(ts + tc::oDc, ts + tc::oAh + j * 8,
+                                           tc::b_desc(sB2_addr + tc::kB2PieceBytes + uint32_t(2 * j) * tc::kLBO2, tc::kLBO2), idesc2, j > 0);
+#pragma unroll
+                        for (int j = 0; j < tc::kK2Steps; j++)
+                            tc::mma_f16_ts(ts + tc::oDc, ts + tc::oAl + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * tc::kLBO2, tc::kLBO2),
+                                           idesc2, 1);
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(&d2_full)));
                     }
-                    float pr[1][C];
-                    mlp_out_chunk<L, 1, kSmem>(wt, 0, h2, pr);
-                    float cost[C];
+                    TC_TRACE(10, warp == tc::kProdWarps && lane == 0);
+                    __syncwarp();
+                    bits |= tr.decide() << tt;                       // metrics entering this stage; overlaps the MMAs
+                    tc::mbar_wait(smem_addr(&d2_full), n & 1, timeout_flag);
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+                    TC_TRACE(11, warp == tc::kProdWarps && lane == 0);
+                    float pm_[16], pc_[16];
+                    tc::tmem_ld16(slot_lane + tc::oDm, pm_);
+                    tc::tmem_ld16(slot_lane + tc::oDc, pc_);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;");
+                    asm volatile("tcgen05.fence::before_thread_sync;");
+                    TC_TRACE(12, warp == tc::kProdWarps && lane == 0);
+                    tc::mbar_arrive(smem_addr(&slot_free[slot]));    // the slot's A and D columns may be refilled
+                    float pr[C], cost[C];
 #pragma unroll
-                    for (int i = 0; i < C; i++) cost[i] = -pr[0][i];  // vnet_detector.py:57
+                    for (int i = 0; i < C; i++) {
+                        pr[i] = fmaf(pc_[i], tc::kInvScale, pm_[i]);
+                        cost[i] = -pr[i];                            // vnet_detector.py:57
+                    }
                     tr.template step_chunk<0>(cost);
                     tr.commit();
+                    TC_TRACE(13, warp == tc::kProdWarps && lane == 0);
                     if (p.priors_out && b < p.B) {
                         float *dst = p.priors_out + (b * p.T + t0 + tt) * S;
 #pragma unroll
-                        for (int i = 0; i < C; i++) dst[i] = pr[0][i];
+                        for (int i = 0; i < C; i++) dst[i] = pr[i];
                     }
                 }
                 __syncwarp();
@@ -358,8 +460,8 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
 
 template <int L>
 constexpr size_t tc_smem_bytes() {
-    return size_t(3) * tc::kBPieceBytes +
-           (size_t(tc::kProdWarps + tc::kConsWarps) * kTileFloats + VnetSmem<L>::kFloats + 4 * (tc::kK / 2)) * sizeof(float);
+    return size_t(2) * tc::kBPieceBytes + 2 * tc::kB2PieceBytes +
+           (size_t(tc::kProdWarps + tc::kConsWarps) * kTileFloats + 4 * (tc::kK / 2)) * sizeof(float);
 }
 
 }  // namespace mvn

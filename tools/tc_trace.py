@@ -1,0 +1,40 @@
+"""Pipeline timeline of the tcgen05 fused kernel (debug library built with -DMVN_TC_TRACE).
+Usage: python tools/tc_trace.py"""
+import ctypes
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import bench
+from meta_viterbinet_b200 import _lib
+
+_lib.LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libmvn_trace.so')
+import meta_viterbinet_b200 as mvn
+
+dev = torch.device('cuda', 0)
+w = bench.make_weights(torch, dev)
+bits, y = bench.synth_frames(torch, dev, 148 * 128 * 4, 10, 1)
+for _ in range(2):
+    mvn.ops.vnet_decode(y, w)
+torch.cuda.synchronize()
+lib = _lib.load()
+buf = (ctypes.c_longlong * (64 * 16))()
+lib.mvn_debug_tc_trace(buf)
+t = np.array(buf[:]).reshape(64, 16)
+names = ['P start', 'P computed', 'P slot acquired', 'P stored', 'M a_full seen', 'M issued', 'C wait d_full', 'C d_full seen',
+         'C h2->tmem done', 'C barrier passed', 'C mma2 issued', 'C d2_full seen', 'C slot released', 'C acs done']
+base = t[8, 0]
+print('stage ' + ' '.join(f'{n[:12]:>13s}' for n in names))
+for s in range(8, 24):
+    print(f'{s:5d} ' + ' '.join(f'{int(t[s, e] - base):13d}' for e in range(14)))
+d = lambda a, b: float(np.median(t[16:56, b] - t[16:56, a]))
+print('\nmedian segment lengths (cycles), stages 16..55:')
+for a, b, label in [(0, 1, 'producer compute'), (1, 2, 'producer waits for slot'), (2, 3, 'producer tcgen05.st + wait::st'),
+                    (3, 4, 'a_full arrive -> MMA warp wakes'), (4, 5, 'MMA warp issues 21 MMAs'), (5, 7, 'commit -> consumer sees d_full'),
+                    (7, 8, 'consumer: ld D, relu, split, st A2'), (8, 9, 'consumer barrier'), (9, 10, 'issue 12 layer-3 MMAs'),
+                    (10, 11, 'layer-3 MMAs -> d2_full seen'), (11, 12, 'ld priors, release slot'), (12, 13, 'ACS'), (6, 7, 'consumer idle waiting for d_full')]:
+    print(f'  {label:40s} {d(a, b):8.0f}')
+print(f'  stage period (consumer)                  {float(np.median(np.diff(t[16:56, 13]))):8.0f}')

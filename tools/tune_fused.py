@@ -18,7 +18,7 @@ bits, y = bench.synth_frames(torch, dev, frames, 10, 1)
 lib = _lib.load()
 lib.mvn_debug_set_variant.restype = ctypes.c_int
 lib.mvn_debug_set_variant.argtypes = [ctypes.c_int]
-names = {4: 'fma const M2 384 u10', 1: 'fma smem M2 256 u10', 2: 'fma const M2 320 u10', 3: 'tcgen05 warp-specialised bf16x6 (default)'}
+names = {4: 'fma const M2 384 u10', 1: 'fma smem M2 256 u10', 2: 'fma const M2 320 u10', 3: 'tcgen05 warp-specialised fp16x2 (default)'}
 ref = None
 for v in (4, 1, 3):
     lib.mvn_debug_set_variant(v)
