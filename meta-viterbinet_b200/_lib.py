@@ -5,7 +5,7 @@ call raises.  torch is used only for device memory and the current stream.
 """
 import ctypes
 import os
-from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_void_p, POINTER
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_uint64, c_void_p, POINTER
 
 import torch
 
@@ -41,6 +41,11 @@ _PROTOS = {
     'mvn_ctx_vnet_decode_host': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     'mvn_ctx_va_decode_host': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     'mvn_launch_count': (c_int64, [c_int]),
+    # include/mvn_b200_next.h
+    'mvn_channel_transmit': (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_double, c_void_p, c_uint64,
+                                     c_void_p, c_void_p]),
+    'mvn_traceback': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'mvn_va_cost': (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     'mvn_fp32_peak': (c_int, [c_int, c_int, POINTER(c_double), POINTER(c_double), c_void_p]),
 }
 

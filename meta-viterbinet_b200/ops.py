@@ -167,3 +167,56 @@ def unpack_bits(words, T):
     shifts = torch.arange(32, device=words.device, dtype=torch.int32)
     bits = (words.unsqueeze(-1) >> shifts) & 1
     return bits.reshape(words.shape[0], -1)[:, :T].float()
+
+
+# ------------------------------------------------------------------ SURVEY.md §8(f) "next" rows
+def _bind_next():
+    return load()
+
+
+def channel_transmit(bits, taps, snr_db, noise=None, seed=0):
+    """ISI-AWGN channel on the device (channel_dataset.py:71,87-95 + channel.py:12-35): bits [B,T] 0/1 ->
+    y [B,T] fp32.  taps [n_h, L] float64 (n_h = 1 or B, or any divisor pattern b mod n_h); noise [B,T] float64
+    standard-normal samples for exact parity with a reference run, else Philox on the device with `seed`."""
+    lib = _bind_next()
+    bits = dev_f32(bits)
+    B, T = bits.shape
+    taps = torch.as_tensor(taps, dtype=torch.float64).to(bits.device).contiguous()
+    if taps.dim() == 1:
+        taps = taps.unsqueeze(0)
+    n_h, L = taps.shape
+    nz = None
+    if noise is not None:
+        nz = torch.as_tensor(noise, dtype=torch.float64).to(bits.device).contiguous()
+        if tuple(nz.shape) != (B, T):
+            raise ValueError('noise must be [B,T]')
+    y = torch.empty((B, T), dtype=torch.float32, device=bits.device)
+    check(lib.mvn_channel_transmit(ptr(bits), B, T, L, ptr(taps), n_h, float(snr_db), ptr(nz), int(seed), ptr(y), stream()))
+    return y
+
+
+def mlse_decode(cost, n_stages=None, terminated=False, out_format=OUT_F32):
+    """True-MLSE decoding of cost [B,T,S] by survivor traceback (the mode SURVEY.md §8f ranks 3rd; the reference's own
+    rule is acs_decode).  terminated=True starts the traceback from state 0 (zero-padded words), else from the best
+    final state."""
+    lib = _bind_next()
+    cost = dev_f32(cost)
+    B, T, S = cost.shape
+    L = _mem_len(S)
+    n = T if n_stages is None else int(n_stages)
+    _, pm, surv = acs_decode(cost, n, return_final_pm=True, return_survivors=True)
+    dec = _new_out(B, T, out_format, cost.device)
+    check(lib.mvn_traceback(ptr(surv), ptr(pm), B, T, n, L, 0 if terminated else -1, out_format, ptr(dec), stream()))
+    return dec
+
+
+def va_mlse_decode(y, state_priors, n_stages=None, terminated=True, out_format=OUT_F32):
+    """Full-CSI Viterbi with traceback: branch metrics as in va_decode, decisions by MLSE."""
+    lib = _bind_next()
+    y = dev_f32(y)
+    sp = dev_f32(state_priors)
+    B, T = y.shape
+    n_h, S = sp.shape
+    cost = torch.empty((B, T, S), dtype=torch.float32, device=y.device)
+    check(lib.mvn_va_cost(ptr(y), B, T, _mem_len(S), ptr(sp), n_h, ptr(cost), stream()))
+    return mlse_decode(cost, n_stages, terminated, out_format)

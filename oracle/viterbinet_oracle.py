@@ -69,6 +69,37 @@ def acs_decode(cost: np.ndarray, n_stages: Optional[int] = None,
     return dec, pm
 
 
+def mlse_decode(cost: np.ndarray, n_stages: Optional[int] = None, start_state: int = -1):
+    """SURVEY.md §8(f)3 — true MLSE over the reference trellis by survivor traceback (the indices
+    trellis_utils.py:30 returns).  State(t) = sum_i b[t+i] 2^i, so the predecessor of j is (2j+sigma) mod S and the
+    survivor choice sigma is the transmitted bit b[t].  start_state < 0: best final state (lowest index on ties).
+    Returns (decoded fp32 [B,T], states int [B,n+1] along the surviving path, final pm)."""
+    cost = np.asarray(cost, dtype=F32)
+    B, T, S = cost.shape
+    n = T if n_stages is None else n_stages
+    _, pm, surv = acs_decode(cost, n, return_survivors=True)
+    dec = np.zeros((B, T), dtype=F32)
+    states = np.zeros((B, n + 1), dtype=np.int64)
+    j = np.argmin(pm, axis=1) if start_state < 0 else np.full(B, start_state)
+    states[:, n] = j
+    rows = np.arange(B)
+    for t in range(n - 1, -1, -1):
+        sigma = surv[rows, t, j].astype(np.int64)
+        j = (2 * j + sigma) % S
+        dec[:, t] = sigma
+        states[:, t] = j
+    return dec, states, pm
+
+
+def path_cost(cost: np.ndarray, states: np.ndarray) -> np.ndarray:
+    """fp32 metric of a state sequence accumulated stage by stage like the ACS recursion does."""
+    B, n = states.shape[0], states.shape[1] - 1
+    acc = np.zeros(B, dtype=F32)
+    for t in range(n):
+        acc = (acc + cost[np.arange(B), t, states[:, t]]).astype(F32)
+    return acc
+
+
 # --------------------------------------------------------------------------------------
 # a4 / a5 — classical VA with full CSI
 # --------------------------------------------------------------------------------------

@@ -460,3 +460,74 @@ def test_sweep_on_gpu_counts(mvn):
         c = mvn.sweep.run_sweep([8.0, 10.0], 300, block, device='cuda', rank=r, world_size=4)
         parts += c
     assert torch.equal(parts, total)
+
+
+# ------------------------------------------------------------------------------- SURVEY.md §8(f) next rows
+@pytest.mark.parametrize('L', [3, 4, 6])
+def test_channel_transmit_matches_reference_channel(mvn, L):
+    rng = np.random.RandomState(L)
+    B, T = 37, 136
+    bits = rng.randint(0, 2, size=(B, T))
+    h = np.abs(rng.randn(B, L)) + 0.1                      # one tap vector per word (fading)
+    noise = rng.normal(0, 1, (B, T))
+    ref = np.zeros((B, T))
+    c = np.concatenate([bits, np.zeros((B, L))], axis=1)
+    s = 1 - 2 * c
+    for i in range(L):
+        ref += h[:, L - 1 - i:L - i] * s[:, i:i + T]
+    ref = (ref + (10 ** (9.0 / 10)) ** (-0.5) * noise).astype(np.float32)
+    y = mvn.ops.channel_transmit(cu(bits.astype(np.float32)), h, 9.0, noise=noise)
+    assert np.array_equal(y.cpu().numpy(), ref)
+    # static channel (one tap row) through the oracle's restatement
+    rng2 = np.random.RandomState(7)
+    h1 = np.exp(-0.2 * np.arange(L)).reshape(1, L)
+    n2 = rng2.normal(0, 1, (B, T))
+    ref2 = orc.isi_awgn(bits, h1, 10.0, L, np.random.RandomState(7)).astype(np.float32)
+    y2 = mvn.ops.channel_transmit(cu(bits.astype(np.float32)), h1, 10.0, noise=n2)
+    assert np.array_equal(y2.cpu().numpy(), ref2)
+
+
+def test_channel_transmit_device_noise_statistics(mvn):
+    B, T, L, snr = 4096, 120, 4, 6.0
+    bits = torch.zeros(B, T).cuda()
+    h = np.array([[1.0, 0.0, 0.0, 0.0]])
+    y = mvn.ops.channel_transmit(bits, h, snr, seed=123)
+    n = (y - 1.0).double()                                 # all-zero bits -> symbol +1 on the main tap
+    sigma = 10 ** (-snr / 20)
+    assert abs(float(n.mean())) < 5 * sigma / np.sqrt(B * T)
+    assert abs(float(n.std()) / sigma - 1) < 0.01
+    y2 = mvn.ops.channel_transmit(bits, h, snr, seed=123)
+    assert torch.equal(y, y2)                              # reproducible for a seed
+    assert not torch.equal(y, mvn.ops.channel_transmit(bits, h, snr, seed=124))
+
+
+@pytest.mark.parametrize('L', [1, 3, 4, 5, 6, 8])
+def test_mlse_traceback_vs_oracle(mvn, L):
+    rng = np.random.RandomState(L)
+    S, B, T = 2 ** L, 45, 50
+    cost = (rng.randn(B, T, S) * 2).astype(np.float32)
+    cost[::4] = rng.randint(0, 3, size=cost[::4].shape)
+    for n_stages, start in ((T, -1), (T - 7, -1), (T, 0)):
+        ref, _, _ = orc.mlse_decode(cost, n_stages, start)
+        dec = mvn.ops.mlse_decode(cu(cost), n_stages, terminated=(start == 0))
+        assert np.array_equal(dec.cpu().numpy(), ref)
+    words = mvn.ops.mlse_decode(cu(cost), out_format=mvn.OUT_BITS)
+    assert np.array_equal(mvn.ops.unpack_bits(words, T).cpu().numpy(), orc.mlse_decode(cost)[0])
+
+
+def test_va_mlse_beats_the_reference_rule(mvn):
+    """Traceback is strictly better than the reference's running-argmin rule on the same channel."""
+    from meta_viterbinet_b200.channel_taps import state_priors_table
+    rng = np.random.RandomState(3)
+    L, B, T = 4, 4000, 120
+    h = np.exp(-0.2 * np.arange(L)).reshape(1, L)
+    bits = rng.randint(0, 2, size=(B, T))
+    y = mvn.ops.channel_transmit(cu(bits.astype(np.float32)), h, 8.0, seed=5)
+    table = cu(state_priors_table(h, L))
+    ref_rule = mvn.ops.va_decode(y, table).cpu().numpy()
+    mlse = mvn.ops.va_mlse_decode(y, table, terminated=True).cpu().numpy()
+    cost = orc.va_cost(y.cpu().numpy(), orc.va_state_priors(h, L))
+    assert np.array_equal(mlse, orc.mlse_decode(cost, start_state=0)[0])
+    ber_rule = (ref_rule != bits)[:, 1:].mean()
+    ber_mlse = (mlse != bits).mean()
+    assert ber_mlse < 0.5 * ber_rule

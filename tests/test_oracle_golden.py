@@ -171,3 +171,27 @@ def test_torch_port_matches_oracle():
     with torch.no_grad():
         dec = tp.va_forward_val(torch.tensor(gv[f'{name}_y']), torch.tensor(sp), int(gv[f'{name}_meta'][1])).numpy()
     assert np.array_equal(dec, gv[f'{name}_dec'])
+
+
+@pytest.mark.parametrize('L', [2, 3, 4])
+def test_mlse_traceback_is_the_minimum_cost_path(L):
+    """The oracle's traceback path attains the final minimum metric exactly, and no other bit sequence is cheaper
+    (brute force over all sequences for a short trellis)."""
+    import itertools
+    rng = np.random.RandomState(L)
+    S, T, B = 2 ** L, 7, 3
+    cost = rng.randn(B, T, S).astype(np.float32)
+    cost[1] = rng.randint(0, 3, size=(T, S))            # ties
+    dec, states, pm = orc.mlse_decode(cost)
+    assert np.array_equal(orc.path_cost(cost, states), pm.min(axis=1))
+    assert np.array_equal(dec, (states[:, :-1] & 1).astype(np.float32))
+    for b in range(B):
+        best = np.inf
+        for bits in itertools.product((0, 1), repeat=T + L - 1):
+            st = [sum(bits[t + i] << i for i in range(L)) for t in range(T)]
+            best = min(best, float(orc.path_cost(cost[b:b + 1], np.array([st + [0]]))[0]))
+        assert best == float(pm[b].min())
+    # terminated variant: forced final state 0
+    dec0, states0, _ = orc.mlse_decode(cost, start_state=0)
+    assert np.all(states0[:, -1] == 0)
+    assert np.array_equal(orc.path_cost(cost, states0), pm[:, 0])
