@@ -205,6 +205,8 @@ __global__ void __launch_bounds__(NT, (L <= 5) ? 4 : 1) va_decode_kernel(VaParam
             uint32_t bits = 0;
             const int t_end = min(32, p.n_stages - t0);
             if (t_end > 0) {
+                // (prefetching the next tile into registers was measured slower: 271 vs 300 G sym/s — the extra
+                //  32 registers cost a resident CTA and the kernel is issue-bound, not latency-bound)
                 warp_load_tile(p.y, p.B, p.T, p.T, row0, t0, tile, lane, vec_in);
                 for (int tt = 0; tt < t_end; tt++) {
                     const float yv = row[tt];

@@ -9,7 +9,7 @@ import subprocess
 import sys
 
 LIB = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'meta-viterbinet_b200', 'libmvn_b200.so')
-DEFAULTS = {1: (1, 448), 2: (1, 448), 3: (1, 448), 4: (1, 384), 5: (1, 384)}
+DEFAULTS = {1: (1, 448), 2: (1, 448), 3: (1, 448), 4: (1, 384), 5: (1, 384)}   # the FMA variant of every L <= 5
 
 
 def hot_loop(lines):
