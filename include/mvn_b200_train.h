@@ -53,6 +53,16 @@ int64_t mvn_priors_backward_workspace_bytes(int L, int64_t N);
 int mvn_vnet_priors_backward(const float *y, int64_t N, int L, const float *theta, const float *grad_priors,
                              float *grad_theta, void *workspace, void *stream);
 
+/* ---- double backward (torch.autograd.grad(..., create_graph=True) of the support loss, trainer.py:437;
+ * the query loss is then differentiated through the fast weights, trainer.py:441-449).
+ * With F(theta, g) = mvn_vnet_priors_backward's result and an upstream u [P]:
+ *   grad_theta2 [P]        = d<u,F>/d theta   (g held fixed)
+ *   grad_grad_priors [N,S] = d<u,F>/d g       (= Jacobian of the priors applied to u)
+ * Same workspace size as the first backward. */
+int mvn_vnet_priors_backward2(const float *y, int64_t N, int L, const float *theta, const float *grad_priors,
+                              const float *u, float *grad_theta2, float *grad_grad_priors, void *workspace,
+                              void *stream);
+
 #ifdef __cplusplus
 }
 #endif

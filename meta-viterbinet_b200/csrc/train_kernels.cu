@@ -49,7 +49,7 @@ __device__ __forceinline__ float sigmoidf_acc(float a) { return 1.f / (1.f + exp
 template <int S, bool TAN>
 __device__ __forceinline__ float symbol_pass(const float *__restrict__ th, const float *__restrict__ tv, float y,
                                              int label, const float *__restrict__ dz_ext, float inv_n,
-                                             float *__restrict__ row) {
+                                             float *__restrict__ row, float *__restrict__ rz_out = nullptr) {
     using TV = ThetaView<S>;
     using SL = Slab<S>;
     float *rt = row + SL::kHalf;  // tangent half of the row
@@ -101,9 +101,15 @@ __device__ __forceinline__ float symbol_pass(const float *__restrict__ th, const
     // softmax cross-entropy (torch CrossEntropyLoss, mean reduction -> 1/N folded into dz)
     float dz[S], rdz[TAN ? S : 1];
     float loss = 0.f;
-    if (dz_ext) {
+    if (dz_ext) {  // upstream gradient is an independent input: its tangent is zero
 #pragma unroll
-        for (int s = 0; s < S; s++) dz[s] = dz_ext[s];
+        for (int s = 0; s < S; s++) {
+            dz[s] = dz_ext[s];
+            if (TAN) {
+                rdz[s] = 0.f;
+                if (rz_out) rz_out[s] = rz[s];
+            }
+        }
     } else {
         float m = z[0];
 #pragma unroll
@@ -381,6 +387,43 @@ __global__ void __launch_bounds__(kTrainThreads, 1) priors_backward_kernel(const
     }
 }
 
+// double backward: for F(theta, g) = J(theta)^T g (the kernel above) and an upstream u [P]:
+//   d<u,F>/dg     = J u                      -> grad_gp [N,S]   (forward tangent of the priors along u)
+//   d<u,F>/dtheta = R_u{ J(theta)^T g }      -> grad_theta2 [P] (forward-over-reverse, g held fixed)
+// This is what torch.autograd.grad(..., create_graph=True) in trainer.py:437 differentiates through.
+template <int S>
+__global__ void __launch_bounds__(kTrainThreads, 1) priors_backward2_kernel(const float *__restrict__ y, int64_t N,
+                                                                           const float *__restrict__ theta,
+                                                                           const float *__restrict__ grad_priors,
+                                                                           const float *__restrict__ u, float *grad_theta2,
+                                                                           float *__restrict__ grad_gp, float *workspace) {
+    using TV = ThetaView<S>;
+    constexpr int P = TV::P, PP = (P + 3) / 4 * 4;
+    extern __shared__ __align__(16) float sm[];
+    float *th = sm;
+    float *tu = sm + PP;
+    float *ysm = tu + PP;
+    float *slab = workspace + size_t(blockIdx.x) * kTrainThreads * Slab<S>::kRow;
+    for (int i = threadIdx.x; i < P; i += kTrainThreads) {
+        th[i] = theta[i];
+        tu[i] = u[i];
+    }
+    __syncthreads();
+    for (int64_t base = int64_t(blockIdx.x) * kTrainThreads; base < N; base += int64_t(gridDim.x) * kTrainThreads) {
+        const int cnt = int(min((long long)kTrainThreads, (long long)(N - base)));
+        if (int(threadIdx.x) < cnt) {
+            const float yv = y[base + threadIdx.x];
+            ysm[threadIdx.x] = yv;
+            symbol_pass<S, true>(th, tu, yv, 0, grad_priors + (base + threadIdx.x) * S, 1.f,
+                                 slab + size_t(threadIdx.x) * Slab<S>::kRow, grad_gp + (base + threadIdx.x) * S);
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < P; idx += kTrainThreads)
+            atomicAdd(grad_theta2 + idx, param_grad<S, true>(idx, slab, ysm, cnt));
+        __syncthreads();
+    }
+}
+
 static int train_grid(int R) { return std::max(1, std::min(R, 2 * sm_count())); }
 
 template <int S>
@@ -418,6 +461,22 @@ static int launch_priors_bwd(const float *y, int64_t N, const float *theta, cons
     MVN_CUDA(cudaMemsetAsync(gt, 0, P * sizeof(float), st));
     const int grid = int(std::max<int64_t>(1, std::min<int64_t>((N + kTrainThreads - 1) / kTrainThreads, 2 * sm_count())));
     kern<<<grid, kTrainThreads, smem, st>>>(y, N, theta, gp, gt, ws);
+    note_launch();
+    MVN_CUDA(cudaGetLastError());
+    return MVN_OK;
+}
+
+template <int L>
+static int launch_priors_bwd2(const float *y, int64_t N, const float *theta, const float *gp, const float *u, float *gt2,
+                              float *ggp, float *ws, cudaStream_t st) {
+    constexpr int S = 1 << L;
+    constexpr int P = ThetaView<S>::P;
+    const size_t smem = (size_t(2) * ((P + 3) / 4 * 4) + kTrainThreads) * sizeof(float);
+    auto kern = priors_backward2_kernel<S>;
+    MVN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    MVN_CUDA(cudaMemsetAsync(gt2, 0, P * sizeof(float), st));
+    const int grid = int(std::max<int64_t>(1, std::min<int64_t>((N + kTrainThreads - 1) / kTrainThreads, 2 * sm_count())));
+    kern<<<grid, kTrainThreads, smem, st>>>(y, N, theta, gp, u, gt2, ggp, ws);
     note_launch();
     MVN_CUDA(cudaGetLastError());
     return MVN_OK;
@@ -504,4 +563,16 @@ extern "C" int mvn_vnet_priors_backward(const float *y, int64_t N, int L, const 
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     MVN_TRAIN_DISPATCH(L, launch_priors_bwd, y, N, theta, grad_priors, grad_theta, static_cast<float *>(workspace), st)
+}
+
+extern "C" int mvn_vnet_priors_backward2(const float *y, int64_t N, int L, const float *theta, const float *grad_priors,
+                                         const float *u, float *grad_theta2, float *grad_grad_priors, void *workspace,
+                                         void *stream) {
+    if (N < 0 || !theta || !u || !grad_theta2 || !workspace || (N > 0 && (!y || !grad_priors || !grad_grad_priors))) {
+        set_error("mvn_vnet_priors_backward2: bad argument");
+        return MVN_ERR_ARG;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MVN_TRAIN_DISPATCH(L, launch_priors_bwd2, y, N, theta, grad_priors, u, grad_theta2, grad_grad_priors,
+                       static_cast<float *>(workspace), st)
 }

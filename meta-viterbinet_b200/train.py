@@ -30,6 +30,7 @@ _PROTOS = {
                                                          c_void_p, c_void_p, c_void_p]),
     'mvn_priors_backward_workspace_bytes': (c_int64, [c_int, c_int64]),
     'mvn_vnet_priors_backward': (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'mvn_vnet_priors_backward2': (c_int, [c_void_p, c_int64, c_int] + [c_void_p] * 7),
 }
 _lib._PROTOS.update(_PROTOS)
 if _lib._lib is not None:          # library already loaded: bind the extra prototypes now
@@ -124,19 +125,34 @@ class BatchedVNetTrainer:
         return (loss, grad) if return_grad else loss
 
 
-def priors_backward(saved, grad_priors):
-    """autograd backward of priors_function: gradients w.r.t. the six weight tensors (none for y)."""
-    y, w1, b1, w2, b2, w3, b3 = saved
-    S = b3.numel()
+def _bwd_args(y, weights, grad_priors):
+    S = weights[5].numel()
     L = S.bit_length() - 1
-    theta = pack_params([w1, b1, w2, b2, w3, b3]).contiguous()
+    theta = pack_params(weights).contiguous()
     g = dev_f32(grad_priors).reshape(-1, S)
     yf = dev_f32(y).reshape(-1)
     nbytes = int(load().mvn_priors_backward_workspace_bytes(L, yf.numel()))
     if nbytes < 0:
         raise _lib.MVNError(f'priors backward supports memory_length 1..5, got {L}')
     ws = torch.empty(nbytes // 4, dtype=torch.float32, device=yf.device)
+    return S, L, theta, g, yf, ws
+
+
+def priors_backward(y, weights, grad_priors):
+    """Backward of the 'train'-phase priors: gradients w.r.t. [W1,b1,W2,b2,W3,b3] (shaped like them)."""
+    S, L, theta, g, yf, ws = _bwd_args(y, weights, grad_priors)
     gt = torch.empty_like(theta)
     check(load().mvn_vnet_priors_backward(ptr(yf), yf.numel(), L, ptr(theta), ptr(g), ptr(gt), ptr(ws), stream()))
-    gw = unpack_params(gt, S)
-    return (None,) + tuple(a.reshape(w.shape) for a, w in zip(gw, [w1, b1, w2, b2, w3, b3]))
+    return tuple(a.reshape(w.shape) for a, w in zip(unpack_params(gt, S), weights))
+
+
+def priors_backward2(y, weights, grad_priors, upstream):
+    """Backward of priors_backward (MAML, trainer.py:437 create_graph=True).  upstream: six tensors shaped like
+    the weights.  Returns (grad w.r.t. grad_priors, six grads w.r.t. the weights)."""
+    S, L, theta, g, yf, ws = _bwd_args(y, weights, grad_priors)
+    u = pack_params(upstream).contiguous()
+    gt2 = torch.empty_like(theta)
+    ggp = torch.empty_like(g)
+    check(load().mvn_vnet_priors_backward2(ptr(yf), yf.numel(), L, ptr(theta), ptr(g), ptr(u), ptr(gt2), ptr(ggp), ptr(ws),
+                                           stream()))
+    return ggp.reshape(grad_priors.shape), tuple(a.reshape(w.shape) for a, w in zip(unpack_params(gt2, S), weights))

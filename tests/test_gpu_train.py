@@ -132,6 +132,76 @@ def test_train_phase_autograd_matches_torch(mvn):
         assert np.max(np.abs(a.cpu().numpy().reshape(-1) - r.reshape(-1))) < 2e-5 * np.max(np.abs(r)) + 1e-9
 
 
+@pytest.mark.parametrize('tag,second', [('maml', True), ('fo', False)])
+def test_meta_train_loop_through_autograd(mvn, tag, second):
+    """trainer.py:425-453 verbatim in structure (functional detector, autograd.grad with create_graph=MAML,
+    fast weights, query loss, Adam) on OUR detectors reproduces the reference's recorded run: the double backward
+    of the CUDA priors is what makes the second-order case work."""
+    g = load_golden('meta')
+    y, tx = cu(g[f'{tag}_y']), cu(g[f'{tag}_tx'])
+    T = y.shape[1]
+    det = mvn.VNETDetector(16, {'val': T, 'train': T})
+    meta = mvn.META_VNETDetector(16, {'val': T, 'train': T})
+    with torch.no_grad():
+        for p, i in zip(det.parameters(), range(6)):
+            p.copy_(cu(g[f'{tag}_w0_{i}']))
+    opt = torch.optim.Adam(det.parameters(), lr=1e-3)
+    crit = torch.nn.CrossEntropyLoss()
+
+    def calc_loss(soft, words):
+        return crit(soft.reshape(-1, 16), mvn.calculate_states(4, words))
+
+    for step, j in enumerate(g[f'{tag}_jhat']):
+        params = list(det.parameters())
+        loss_s = calc_loss(meta(y[j - 1:j], 'train', params), tx[j - 1:j])
+        local = torch.autograd.grad(loss_s, params, create_graph=second)
+        fast = [p - 0.1 * gr for gr, p in zip(local, params)]
+        loss_q = calc_loss(meta(y[j:j + 1], 'train', fast), tx[j:j + 1])
+        meta_grad = torch.autograd.grad(loss_q, params)
+        ref_loss = g[f'{tag}_loss_q'][step]
+        assert abs(float(loss_q) - ref_loss) < 1e-5 * abs(ref_loss)
+        if step == 0:
+            for i, a in enumerate(meta_grad):
+                ref = g[f'{tag}_g1_{i}']
+                assert np.max(np.abs(a.cpu().numpy() - ref)) < 2e-5 * np.max(np.abs(ref)) + 1e-9
+        for p, a in zip(params, meta_grad):
+            p.grad = a
+        opt.step()
+        got = pack([p.detach().cpu().numpy() for p in det.parameters()])
+        assert_close_params(got, [g[f'{tag}_w{step + 1}_{i}'] for i in range(6)], 2e-5)
+
+
+@pytest.mark.parametrize('L', [1, 2, 3, 5])
+def test_double_backward_matches_torch(mvn, L):
+    """gradient of <u, d loss/d theta> w.r.t. theta (through our kernels) == the same through a torch fp64 net."""
+    S = 1 << L
+    rng = np.random.default_rng(40 + L)
+    n = 300
+    y = rng.normal(size=n).astype(np.float32) * 1.5
+    lab = rng.integers(0, S, size=n)
+    ws = [rng.normal(size=s).astype(np.float32) * sc for s, sc in
+          [((100, 1), 1.0), ((100,), 0.5), ((50, 100), 0.15), ((50,), 0.1), ((S, 50), 0.2), ((S,), 0.1)]]
+    us = [rng.normal(size=w.shape).astype(np.float32) for w in ws]
+
+    def run(fwd, dt, dev):
+        var = [torch.tensor(w, dtype=dt, device=dev, requires_grad=True) for w in ws]
+        yy = torch.tensor(y, dtype=dt, device=dev)
+        loss = torch.nn.functional.cross_entropy(fwd(yy, var), torch.tensor(lab, device=dev))
+        gr = torch.autograd.grad(loss, var, create_graph=True)
+        inner = sum((a * torch.tensor(u, dtype=dt, device=dev)).sum() for a, u in zip(gr, us))
+        return [t.detach().cpu().numpy().astype(np.float64) for t in torch.autograd.grad(inner, var)]
+
+    def torch_fwd(yy, v):
+        h1 = torch.sigmoid(yy.reshape(-1, 1) @ v[0].t() + v[1])
+        return torch.relu(h1 @ v[2].t() + v[3]) @ v[4].t() + v[5]
+
+    meta = mvn.META_VNETDetector(S, {'val': n, 'train': n})
+    ours = run(lambda yy, v: meta(yy.reshape(1, -1), 'train', v).reshape(-1, S), torch.float32, 'cuda')
+    ref = run(torch_fwd, torch.float64, 'cpu')
+    for a, r in zip(ours, ref):
+        assert np.max(np.abs(a - r)) < 5e-5 * np.max(np.abs(r)) + 1e-8, (np.max(np.abs(a - r)), np.max(np.abs(r)))
+
+
 def test_training_rejects_unsupported_trellis(mvn):
     with pytest.raises(mvn.MVNError):
         mvn.BatchedVNetTrainer(torch.zeros(1, mvn.train.param_count(7)).cuda(), 7)
