@@ -302,7 +302,7 @@ __device__ int g_tc_timeout = 0;
 __device__ long long g_tc_trace[64 * 16];
 #endif
 
-// tcgen05 variant (memory_length <= 4): every CTA stages its own weights (W2/b2 as bf16 pieces, the rest fp32).
+// tcgen05 variant (memory_length <= 6): every CTA stages its own weights (W2/b2 as bf16 pieces, the rest fp32).
 template <int L>
 static int launch_tc(VnetParams p, cudaStream_t st) {
     const size_t smem = tc_smem_bytes<L>();
@@ -324,7 +324,7 @@ static int launch_tc(VnetParams p, cudaStream_t st) {
 }
 
 // Default variants, picked by tools/tune_fused.py on a B200 (profiles/r01_tune_fused.txt):
-//   L 1..4: tcgen05 variant (vnet_tc_kernel.cuh): layers 2-3 on the tensor cores with an fp16 two-piece split;
+//   L 1..6: tcgen05 variant (vnet_tc_kernel.cuh): layers 2-3 on the tensor cores with an fp16 two-piece split;
 //           the FP32-FMA variants below stay selectable (mvn_debug_set_variant / ops.set_fused_variant)
 //   L 4..5: (FMA) constant-bank weights, 2 frames per lane, 384 threads (3 warps per scheduler), unroll 10
 //   L 1..3: (FMA) same with 448 threads.  ptxas only routes the weight stream through uniform registers
@@ -335,12 +335,15 @@ static int launch_tc(VnetParams p, cudaStream_t st) {
 //   L = 8 : as above with one frame per lane (the path metrics take 131 KB of shared memory)
 template <int L>
 static int launch_fused(const VnetParams &p, cudaStream_t st) {
+    const bool want_fma = g_variant == 1 || g_variant == 2 || g_variant == 4;
+    if constexpr (L <= 6) {
+        if (!want_fma) return launch_tc<L>(p, st);  // 0 (auto) and 3
+    }
     if constexpr (L <= 4) {
         switch (g_variant) {
             case 1: return launch_variant<L, FusedVariant<L, 2, kSmem, 256, 10>>(p, st);
             case 2: return launch_variant<L, FusedVariant<L, 2, kConst, 320, 10>>(p, st);
-            case 4: return launch_variant<L, FusedVariant<L, 2, kConst, (L <= 3 ? 448 : 384), 10>>(p, st);
-            default: return launch_tc<L>(p, st);  // 0 (auto) and 3
+            default: return launch_variant<L, FusedVariant<L, 2, kConst, (L <= 3 ? 448 : 384), 10>>(p, st);
         }
     } else if constexpr (L == 5) {
         return launch_variant<L, FusedVariant<L, 2, kConst, 384, 10>>(p, st);
@@ -353,7 +356,8 @@ static int launch_fused(const VnetParams &p, cudaStream_t st) {
 
 // frames decoded by one full wave of CTAs (host pipeline chunk sizing)
 int vnet_frames_per_wave(int L) {
-    const int per_cta = L <= 4 ? 128 : L == 5 ? 384 * 2 : L <= 7 ? 128 * 2 : 128;
+    const int per_cta = (L <= 6 && !(g_variant == 1 || g_variant == 2 || g_variant == 4)) ? 128
+                        : L <= 3 ? 448 * 2 : L <= 5 ? 384 * 2 : L <= 7 ? 128 * 2 : 128;
     return per_cta * sm_count();
 }
 

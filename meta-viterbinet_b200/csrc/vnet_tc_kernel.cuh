@@ -1,4 +1,4 @@
-// tcgen05 variant of the fused ViterbiNet kernel (memory_length <= 4): layer 2 of the priors MLP
+// tcgen05 variant of the fused ViterbiNet kernel (memory_length <= 6): layer 2 of the priors MLP
 // ([symbols,100] x [100,50], 85 % of the flops) runs on the 5th-generation tensor cores, everything
 // else (sigmoid, ReLU, layer 3, ACS, decision) stays on the CUDA cores of the same CTA.
 //
@@ -46,9 +46,10 @@ constexpr uint32_t kSBO = 128;                // bytes between 8-row groups alon
 constexpr int kBPieceBytes = (kK / 8) * (kN / 8) * 128;
 constexpr int kProdWarps = 8, kConsWarps = 4, kThreadsTc = 32 * (kProdWarps + kConsWarps + 1);  // + one MMA-issue warp
 // layer 3 on the tensor core as well: D2[128 x 16] = h2[128 x 64] W3^T, K2 = 50 hidden units + bias column, padded
-constexpr int kN2 = 16, kK2 = 64, kK2Steps = kK2 / 16, kA2Cols = kK2 / 2;
-constexpr uint32_t kLBO2 = (kN2 / 8) * 128;
-constexpr int kB2PieceBytes = (kK2 / 8) * (kN2 / 8) * 128;
+// (N2 = max(16, n_states) output columns, so up to 64 states fit the slot's 64-column D regions)
+constexpr int kK2 = 64, kK2Steps = kK2 / 16, kA2Cols = kK2 / 2;
+__host__ __device__ constexpr int n2_of(int S) { return S < 16 ? 16 : S; }
+__host__ __device__ constexpr int b2_piece_bytes(int S) { return (kK2 / 8) * (n2_of(S) / 8) * 128; }
 
 __device__ __forceinline__ void split_f16(float x, uint16_t &hi, uint16_t &lo) {
     const __half h = __float2half_rn(x);
@@ -203,9 +204,11 @@ __device__ __forceinline__ void h2_to_tmem(uint32_t slot_lane) {
 
 template <int L>
 __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetParams p, int *timeout_flag, long long *trace) {
-    static_assert(L <= 4, "tcgen05 variant: register trellis, one layer-3 chunk");
+    static_assert(L <= 6, "tcgen05 variant: the priors of one stage must fit a 64-column TMEM region");
     using D = TrellisDims<L>;
-    constexpr int S = D::S, C = D::C, NW = tc::kProdWarps + tc::kConsWarps;
+    constexpr int S = D::S, C = D::C, NCH = D::NCH, NW = tc::kProdWarps + tc::kConsWarps;
+    constexpr int N2 = tc::n2_of(S), kB2PieceBytes = tc::b2_piece_bytes(S);
+    constexpr uint32_t kLBO2 = (N2 / 8) * 128;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(8) uint64_t d_full[2], slot_free[2], a_full[2], d2_full;
@@ -238,16 +241,16 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
         sP[4 * i + 2] = k < kH1 ? p.w.b1[k] * kNegLog2e : 0.f;
         sP[4 * i + 3] = k + 1 < kH1 ? p.w.b1[k + 1] * kNegLog2e : 0.f;
     }
-    // ---- W3 (and b3 as column k2=50) -> fp16 pieces, canonical K-major layout with N2 = 16 rows (states)
-    for (int idx = tid; idx < tc::kN2 * tc::kK2; idx += tc::kThreadsTc) {
+    // ---- W3 (and b3 as column k2=50) -> fp16 pieces, canonical K-major layout with N2 rows (states)
+    for (int idx = tid; idx < N2 * tc::kK2; idx += tc::kThreadsTc) {
         const int n2 = idx / tc::kK2, k = idx % tc::kK2;
         float w = 0.f;
         if (n2 < S) w = k < kH2 ? p.w.w3[n2 * kH2 + k] : (k == kH2 ? p.w.b3[n2] : 0.f);
         uint16_t hi, lo;
         tc::split_f16(w, hi, lo);
-        const int off = (k / 8) * (tc::kN2 / 8) * 128 + (n2 / 8) * 128 + (n2 % 8) * 16 + (k % 8) * 2;
+        const int off = (k / 8) * (N2 / 8) * 128 + (n2 / 8) * 128 + (n2 % 8) * 16 + (k % 8) * 2;
         *reinterpret_cast<uint16_t *>(sB2 + off) = hi;
-        *reinterpret_cast<uint16_t *>(sB2 + tc::kB2PieceBytes + off) = lo;
+        *reinterpret_cast<uint16_t *>(sB2 + kB2PieceBytes + off) = lo;
     }
     if (tid == 0) {
 #pragma unroll
@@ -270,7 +273,7 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
     const uint32_t tmem = tmem_base_s;
     const uint32_t lane_base = uint32_t(quad * 32) << 16;
     const uint32_t sB_addr = smem_addr(sB), sB2_addr = smem_addr(sB2);
-    constexpr uint32_t idesc2 = (1u << 4) | (uint32_t(tc::kN2 >> 3) << 17) | (uint32_t(tc::kM >> 4) << 24);
+    constexpr uint32_t idesc2 = (1u << 4) | (uint32_t(N2 >> 3) << 17) | (uint32_t(tc::kM >> 4) << 24);
     // D=F32, A=B=F16, both K-major, N>>3 at bit 17, M>>4 at bit 24
     constexpr uint32_t idesc = (1u << 4) | (uint32_t(tc::kN >> 3) << 17) | (uint32_t(tc::kM >> 4) << 24);
     const uint32_t sP_addr = smem_addr(sP);
@@ -361,7 +364,9 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
             }
         }
     } else {
-        RegTrellis<L> tr;
+        typename std::conditional<(L <= 5), RegTrellis<L>, SmemTrellis<L>>::type tr;
+        if constexpr (L > 5)   // path metrics of the 128 frames of the tile: [2][H][128] floats behind the W3 pieces
+            tr.init(reinterpret_cast<float *>(sB2 + 2 * kB2PieceBytes), 32 * tc::kConsWarps, (warp - tc::kProdWarps) * 32 + lane);
         ErrAcc acc;
         for (int64_t ct = blockIdx.x; ct < n_cta_tiles; ct += gridDim.x) {
             const int64_t row0 = (ct * 4 + quad) * 32;
@@ -388,15 +393,15 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
                         asm volatile("tcgen05.fence::after_thread_sync;");
 #pragma unroll
                         for (int j = 0; j < tc::kK2Steps; j++)
-                            tc::mma_f16_ts(ts + tc::oDm, ts + tc::oAh + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * tc::kLBO2, tc::kLBO2),
+                            tc::mma_f16_ts(ts + tc::oDm, ts + tc::oAh + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2, kLBO2),
                                            idesc2, j > 0);
 #pragma unroll
                         for (int j = 0; j < tc::kK2Steps; j++)
                             tc::mma_f16_ts(ts + tc::oDc, ts + tc::oAh + j * 8,
-                                           tc::b_desc(sB2_addr + tc::kB2PieceBytes + uint32_t(2 * j) * tc::kLBO2, tc::kLBO2), idesc2, j > 0);
+                                           tc::b_desc(sB2_addr + kB2PieceBytes + uint32_t(2 * j) * kLBO2, kLBO2), idesc2, j > 0);
 #pragma unroll
                         for (int j = 0; j < tc::kK2Steps; j++)
-                            tc::mma_f16_ts(ts + tc::oDc, ts + tc::oAl + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * tc::kLBO2, tc::kLBO2),
+                            tc::mma_f16_ts(ts + tc::oDc, ts + tc::oAl + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2, kLBO2),
                                            idesc2, 1);
                         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(&d2_full)));
                     }
@@ -406,27 +411,40 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
                     tc::mbar_wait(smem_addr(&d2_full), n & 1, timeout_flag);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     TC_TRACE(11, warp == tc::kProdWarps && lane == 0);
-                    float pm_[16], pc_[16];
-                    tc::tmem_ld16(slot_lane + tc::oDm, pm_);
-                    tc::tmem_ld16(slot_lane + tc::oDc, pc_);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;");
-                    asm volatile("tcgen05.fence::before_thread_sync;");
-                    TC_TRACE(12, warp == tc::kProdWarps && lane == 0);
-                    tc::mbar_arrive(smem_addr(&slot_free[slot]));    // the slot's A and D columns may be refilled
-                    float pr[C], cost[C];
+                    float *dst = (p.priors_out && b < p.B) ? p.priors_out + (b * p.T + t0 + tt) * S : nullptr;
+                    // 16 source states per chunk: priors = D_main + D_corr / 2048, cost = -prior (vnet_detector.py:57)
+                    auto chunk = [&](auto cc, bool last) {
+                        constexpr int c = decltype(cc)::value;
+                        float pm_[16], pc_[16];
+                        tc::tmem_ld16(slot_lane + tc::oDm + 16 * c, pm_);
+                        tc::tmem_ld16(slot_lane + tc::oDc + 16 * c, pc_);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;");
+                        if (last) {
+                            asm volatile("tcgen05.fence::before_thread_sync;");
+                            TC_TRACE(12, warp == tc::kProdWarps && lane == 0);
+                            tc::mbar_arrive(smem_addr(&slot_free[slot]));    // the slot's A and D columns may be refilled
+                        }
+                        float pr[C], cost[C];
 #pragma unroll
-                    for (int i = 0; i < C; i++) {
-                        pr[i] = fmaf(pc_[i], tc::kInvScale, pm_[i]);
-                        cost[i] = -pr[i];                            // vnet_detector.py:57
+                        for (int i = 0; i < C; i++) {
+                            pr[i] = fmaf(pc_[i], tc::kInvScale, pm_[i]);
+                            cost[i] = -pr[i];
+                        }
+                        if constexpr (L <= 5) tr.template step_chunk<c>(cost);
+                        else tr.step_chunk_rt(c, cost);
+                        if (dst) {
+#pragma unroll
+                            for (int i = 0; i < C; i++) dst[c * C + i] = pr[i];
+                        }
+                    };
+                    chunk(std::integral_constant<int, 0>{}, NCH == 1);
+                    if constexpr (NCH >= 2) chunk(std::integral_constant<int, 1>{}, NCH == 2);
+                    if constexpr (NCH >= 4) {
+                        chunk(std::integral_constant<int, 2>{}, false);
+                        chunk(std::integral_constant<int, 3>{}, true);
                     }
-                    tr.template step_chunk<0>(cost);
                     tr.commit();
                     TC_TRACE(13, warp == tc::kProdWarps && lane == 0);
-                    if (p.priors_out && b < p.B) {
-                        float *dst = p.priors_out + (b * p.T + t0 + tt) * S;
-#pragma unroll
-                        for (int i = 0; i < C; i++) dst[i] = pr[i];
-                    }
                 }
                 __syncwarp();
                 if (p.decoded) {
@@ -460,8 +478,9 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
 
 template <int L>
 constexpr size_t tc_smem_bytes() {
-    return size_t(2) * tc::kBPieceBytes + 2 * tc::kB2PieceBytes +
-           (size_t(tc::kProdWarps + tc::kConsWarps) * kTileFloats + 4 * (tc::kK / 2)) * sizeof(float);
+    return size_t(2) * tc::kBPieceBytes + 2 * tc::b2_piece_bytes(1 << L) +
+           (size_t(tc::kProdWarps + tc::kConsWarps) * kTileFloats + 4 * (tc::kK / 2)) * sizeof(float) +
+           (L > 5 ? SmemTrellis<L>::bytes(32 * tc::kConsWarps) : 0);
 }
 
 }  // namespace mvn
