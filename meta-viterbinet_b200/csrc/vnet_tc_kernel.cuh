@@ -14,10 +14,11 @@
 // Warp-specialised pipeline over a two-slot TMEM ring; one frame = one TMEM lane, 128 frames per CTA tile:
 //   8 producer warps : y -> 100 sigmoids -> fp16 hi/lo split -> tcgen05.st  A_hi, A_lo [128 x 112] (2 x 56 columns)
 //                      (warps w and w+4 serve the same 32 frames and split the hidden units)
-//   1 MMA warp       : per stage 3 x 7 tcgen05.mma.kind::f16 (M=128, N=64, K=16), A from TMEM, B (W2 pieces) from
-//                      shared memory in the canonical K-major no-swizzle layout; tcgen05.commit -> d_full[slot]
+//   1 MMA warp       : per stage 7 + 7 tcgen05.mma.kind::f16 (M=128, K=16; N=128 for A_hi x [W2_hi | W2_lo], N=64 for
+//                      A_lo x W2_hi), A from TMEM, B from shared memory in the canonical K-major no-swizzle layout;
+//                      tcgen05.commit -> d_full[slot]
 //   4 consumer warps : tcgen05.ld D_main/D_corr -> combine -> ReLU -> the same hi/lo split -> tcgen05.st as the A
-//                      operand of LAYER 3, which also runs on the tensor core (3 x 4 MMAs, N=16, W3 pieces and b3 in
+//                      operand of LAYER 3, which also runs on the tensor core (4 + 4 MMAs, W3 pieces and b3 in
 //                      shared memory, issued by one consumer thread); tcgen05.ld of the 16 priors -> ACS on the
 //                      frame's 8 private path metrics, decision bit, outputs, BER.  No weight traffic on the LSU.
 // The sigmoid/split/MMA work of later stages does not depend on the ACS result of earlier ones (only the
@@ -41,15 +42,19 @@ constexpr int kACols = kK / 2;                // 32-bit TMEM columns per A piece
 constexpr int kSlotCols = 256;                // slot stride; 240 used: D_main | D_corr | A_hi | A_lo
 constexpr int oDm = 0, oDc = kN, oAh = 2 * kN, oAl = 2 * kN + kACols;
 constexpr float kScale = 2048.f, kInvScale = 1.f / 2048.f;
-constexpr uint32_t kLBO = (kN / 8) * 128;     // bytes between consecutive 16-byte K chunks (k-chunk stride)
+// B operand of layer 2: the hi and lo pieces of W2 stacked along N (rows 0..63 hi, 64..127 lo), so ONE N=128 MMA per
+// k-step produces D_main | D_corr side by side; the A_lo x B_hi chain reads rows 0..63 of the same buffer (N=64).
+// Every tcgen05.mma costs >= 48 cycles whatever its N (tools/mma_rate.cu: N<=64 48, N=128 66, N=256 131), so
+// stacking saves a third of the tensor-pipe time of this small-N problem.
+constexpr uint32_t kLBO = (2 * kN / 8) * 128; // bytes between consecutive 16-byte K chunks (k-chunk stride)
 constexpr uint32_t kSBO = 128;                // bytes between 8-row groups along N
-constexpr int kBPieceBytes = (kK / 8) * (kN / 8) * 128;
+constexpr int kBBytes = (kK / 8) * (2 * kN / 8) * 128;
 constexpr int kProdWarps = 8, kConsWarps = 4, kThreadsTc = 32 * (kProdWarps + kConsWarps + 1);  // + one MMA-issue warp
 // layer 3 on the tensor core as well: D2[128 x 16] = h2[128 x 64] W3^T, K2 = 50 hidden units + bias column, padded
 // (N2 = max(16, n_states) output columns, so up to 64 states fit the slot's 64-column D regions)
 constexpr int kK2 = 64, kK2Steps = kK2 / 16, kA2Cols = kK2 / 2;
 __host__ __device__ constexpr int n2_of(int S) { return S < 16 ? 16 : S; }
-__host__ __device__ constexpr int b2_piece_bytes(int S) { return (kK2 / 8) * (n2_of(S) / 8) * 128; }
+__host__ __device__ constexpr int b2_bytes(int S) { return (kK2 / 8) * (2 * n2_of(S) / 8) * 128; }  // hi | lo stacked along N
 
 __device__ __forceinline__ void split_f16(float x, uint16_t &hi, uint16_t &lo) {
     const __half h = __float2half_rn(x);
@@ -207,14 +212,14 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
     static_assert(L <= 6, "tcgen05 variant: the priors of one stage must fit a 64-column TMEM region");
     using D = TrellisDims<L>;
     constexpr int S = D::S, C = D::C, NCH = D::NCH, NW = tc::kProdWarps + tc::kConsWarps;
-    constexpr int N2 = tc::n2_of(S), kB2PieceBytes = tc::b2_piece_bytes(S);
-    constexpr uint32_t kLBO2 = (N2 / 8) * 128;
+    constexpr int N2 = tc::n2_of(S), kB2Bytes = tc::b2_bytes(S);
+    constexpr uint32_t kLBO2 = (2 * N2 / 8) * 128;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(8) uint64_t d_full[2], slot_free[2], a_full[2], d2_full;
     constexpr int NT_TILES = tc::kProdWarps + tc::kConsWarps;                    // producers and consumers stage tiles
-    uint8_t *sB = smem_raw;                                                      // W2 pieces: hi | lo
-    float *tiles = reinterpret_cast<float *>(smem_raw + 2 * tc::kBPieceBytes);   // one 32x32 tile per such warp
+    uint8_t *sB = smem_raw;                                                      // W2 pieces, hi rows | lo rows
+    float *tiles = reinterpret_cast<float *>(smem_raw + tc::kBBytes);            // one 32x32 tile per such warp
     float *sP = tiles + NT_TILES * kTileFloats;                                  // [56][4] pair table for the packed sigmoid
     uint8_t *sB2 = reinterpret_cast<uint8_t *>(sP + 4 * (tc::kK / 2));           // W3 (+ b3 column) pieces: hi | lo
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, quad = warp & 3;
@@ -229,9 +234,9 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
         if (n < kH2) w = k < kH1 ? p.w.w2[n * kH1 + k] : (k == kH1 ? p.w.b2[n] : 0.f);
         uint16_t hi, lo;
         tc::split_f16(w, hi, lo);
-        const int off = (k / 8) * (tc::kN / 8) * 128 + (n / 8) * 128 + (n % 8) * 16 + (k % 8) * 2;
+        const int off = (k / 8) * (2 * tc::kN / 8) * 128 + (n / 8) * 128 + (n % 8) * 16 + (k % 8) * 2;
         *reinterpret_cast<uint16_t *>(sB + off) = hi;
-        *reinterpret_cast<uint16_t *>(sB + tc::kBPieceBytes + off) = lo;
+        *reinterpret_cast<uint16_t *>(sB + off + (tc::kN / 8) * 128) = lo;
     }
     for (int i = tid; i < tc::kK / 2; i += tc::kThreadsTc) {
         const float kNegLog2e = -1.4426950408889634f;
@@ -248,9 +253,9 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
         if (n2 < S) w = k < kH2 ? p.w.w3[n2 * kH2 + k] : (k == kH2 ? p.w.b3[n2] : 0.f);
         uint16_t hi, lo;
         tc::split_f16(w, hi, lo);
-        const int off = (k / 8) * (N2 / 8) * 128 + (n2 / 8) * 128 + (n2 % 8) * 16 + (k % 8) * 2;
+        const int off = (k / 8) * (2 * N2 / 8) * 128 + (n2 / 8) * 128 + (n2 % 8) * 16 + (k % 8) * 2;
         *reinterpret_cast<uint16_t *>(sB2 + off) = hi;
-        *reinterpret_cast<uint16_t *>(sB2 + kB2PieceBytes + off) = lo;
+        *reinterpret_cast<uint16_t *>(sB2 + off + (N2 / 8) * 128) = lo;
     }
     if (tid == 0) {
 #pragma unroll
@@ -273,9 +278,11 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
     const uint32_t tmem = tmem_base_s;
     const uint32_t lane_base = uint32_t(quad * 32) << 16;
     const uint32_t sB_addr = smem_addr(sB), sB2_addr = smem_addr(sB2);
+    // D=F32, A=B=F16, both K-major, N>>3 at bit 17, M>>4 at bit 24; "w" = hi and lo pieces of B side by side
     constexpr uint32_t idesc2 = (1u << 4) | (uint32_t(N2 >> 3) << 17) | (uint32_t(tc::kM >> 4) << 24);
-    // D=F32, A=B=F16, both K-major, N>>3 at bit 17, M>>4 at bit 24
+    constexpr uint32_t idesc2w = (1u << 4) | (uint32_t(2 * N2 >> 3) << 17) | (uint32_t(tc::kM >> 4) << 24);
     constexpr uint32_t idesc = (1u << 4) | (uint32_t(tc::kN >> 3) << 17) | (uint32_t(tc::kM >> 4) << 24);
+    constexpr uint32_t idescw = (1u << 4) | (uint32_t(2 * tc::kN >> 3) << 17) | (uint32_t(tc::kM >> 4) << 24);
     const uint32_t sP_addr = smem_addr(sP);
     const bool vec_in = is_vec_ok(p.y, p.T, p.T);
     const bool vec_out = p.out_format == MVN_OUT_F32 && is_vec_ok(p.decoded, p.T, p.T);
@@ -300,24 +307,26 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
                     // Compute this stage's pieces into registers BEFORE waiting for the slot: the sigmoid/split work
                     // then overlaps the MMAs and the consumer of the stage that still owns the slot.
                     TC_TRACE(0, tid == 0);
-                    constexpr int NCH = 4;                       // k-steps per producer warp (the upper half has 3)
-                    const int c_base = warp < 4 ? 0 : 4;
-                    uint32_t vh[NCH][8], vl[NCH][8];
+                    // k-steps per producer warp: warps 0-3 take steps 0..2 (24 pairs of hidden units), warps 4-7 take
+                    // steps 3..6 (26 pairs + the bias/padding columns), so both halves finish together
+                    constexpr int NKS = 4;
+                    const int c_base = warp < 4 ? 0 : 3;
+                    uint32_t vh[NKS][8], vl[NKS][8];
                     if (warp < 4) {
 #pragma unroll
-                        for (int i = 0; i < 4; i++) tc::compute_chunk<false>(sP_addr, i, yy, vh[i], vl[i]);
+                        for (int i = 0; i < 3; i++) tc::compute_chunk<false>(sP_addr, i, yy, vh[i], vl[i]);
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 2; i++) tc::compute_chunk<false>(sP_addr, 4 + i, yy, vh[i], vl[i]);
-                        tc::compute_chunk<true>(sP_addr, 6, yy, vh[2], vl[2]);
+                        for (int i = 0; i < 3; i++) tc::compute_chunk<false>(sP_addr, 3 + i, yy, vh[i], vl[i]);
+                        tc::compute_chunk<true>(sP_addr, 6, yy, vh[3], vl[3]);
                     }
                     TC_TRACE(1, tid == 0);
                     tc::mbar_wait(smem_addr(&slot_free[slot]), (use & 1) ^ 1, timeout_flag);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     TC_TRACE(2, tid == 0);
 #pragma unroll
-                    for (int i = 0; i < NCH; i++) {
-                        if (warp < 4 || i < 3) {
+                    for (int i = 0; i < NKS; i++) {
+                        if (warp >= 4 || i < 3) {
                             tc::tmem_st8(slot_lane + tc::oAh + (c_base + i) * 8, vh[i]);
                             tc::tmem_st8(slot_lane + tc::oAl + (c_base + i) * 8, vl[i]);
                         }
@@ -332,7 +341,7 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
             }
         }
     } else if (mma_warp) {
-        // one warp does nothing but issue: per stage 3 x 7 MMAs, then tcgen05.commit -> d_full[slot]
+        // one warp does nothing but issue: per stage 7 + 7 MMAs, then tcgen05.commit -> d_full[slot]
         for (int64_t ct = blockIdx.x; ct < n_cta_tiles; ct += gridDim.x) {
             for (int t0 = 0; t0 < p.T; t0 += 32) {
                 const int t_end = min(32, p.n_stages - t0);
@@ -345,15 +354,11 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
                     if (lane == 0) {
                         const uint32_t ts = tmem + slot * tc::kSlotCols;
 #pragma unroll
-                        for (int j = 0; j < tc::kKSteps; j++)   // D_main = A_hi B_hi
-                            tc::mma_f16_ts(ts + tc::oDm, ts + tc::oAh + j * 8, tc::b_desc(sB_addr + uint32_t(2 * j) * tc::kLBO), idesc,
+                        for (int j = 0; j < tc::kKSteps; j++)   // D_main | D_corr = A_hi [B_hi | B_lo]
+                            tc::mma_f16_ts(ts + tc::oDm, ts + tc::oAh + j * 8, tc::b_desc(sB_addr + uint32_t(2 * j) * tc::kLBO), idescw,
                                            j > 0);
 #pragma unroll
-                        for (int j = 0; j < tc::kKSteps; j++)   // D_corr = A_hi B_lo + A_lo B_hi
-                            tc::mma_f16_ts(ts + tc::oDc, ts + tc::oAh + j * 8,
-                                           tc::b_desc(sB_addr + tc::kBPieceBytes + uint32_t(2 * j) * tc::kLBO), idesc, j > 0);
-#pragma unroll
-                        for (int j = 0; j < tc::kKSteps; j++)
+                        for (int j = 0; j < tc::kKSteps; j++)   // D_corr += A_lo B_hi
                             tc::mma_f16_ts(ts + tc::oDc, ts + tc::oAl + j * 8, tc::b_desc(sB_addr + uint32_t(2 * j) * tc::kLBO), idesc, 1);
                         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                             smem_addr(&d_full[slot])));
@@ -366,7 +371,7 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
     } else {
         typename std::conditional<(L <= 5), RegTrellis<L>, SmemTrellis<L>>::type tr;
         if constexpr (L > 5)   // path metrics of the 128 frames of the tile: [2][H][128] floats behind the W3 pieces
-            tr.init(reinterpret_cast<float *>(sB2 + 2 * kB2PieceBytes), 32 * tc::kConsWarps, (warp - tc::kProdWarps) * 32 + lane);
+            tr.init(reinterpret_cast<float *>(sB2 + kB2Bytes), 32 * tc::kConsWarps, (warp - tc::kProdWarps) * 32 + lane);
         ErrAcc acc;
         for (int64_t ct = blockIdx.x; ct < n_cta_tiles; ct += gridDim.x) {
             const int64_t row0 = (ct * 4 + quad) * 32;
@@ -389,19 +394,15 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
                     TC_TRACE(8, warp == tc::kProdWarps && lane == 0);
                     asm volatile("bar.sync 2, %0;" ::"n"(32 * tc::kConsWarps));
                     TC_TRACE(9, warp == tc::kProdWarps && lane == 0);
-                    if (warp == tc::kProdWarps && lane == 0) {       // one consumer thread issues layer 3: 3 x 4 MMAs
+                    if (warp == tc::kProdWarps && lane == 0) {       // one consumer thread issues layer 3: 4 + 4 MMAs
                         asm volatile("tcgen05.fence::after_thread_sync;");
 #pragma unroll
-                        for (int j = 0; j < tc::kK2Steps; j++)
+                        for (int j = 0; j < tc::kK2Steps; j++)   // priors_main | priors_corr = h2_hi [W3_hi | W3_lo]
                             tc::mma_f16_ts(ts + tc::oDm, ts + tc::oAh + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2, kLBO2),
-                                           idesc2, j > 0);
+                                           idesc2w, j > 0);
 #pragma unroll
-                        for (int j = 0; j < tc::kK2Steps; j++)
-                            tc::mma_f16_ts(ts + tc::oDc, ts + tc::oAh + j * 8,
-                                           tc::b_desc(sB2_addr + kB2PieceBytes + uint32_t(2 * j) * kLBO2, kLBO2), idesc2, j > 0);
-#pragma unroll
-                        for (int j = 0; j < tc::kK2Steps; j++)
-                            tc::mma_f16_ts(ts + tc::oDc, ts + tc::oAl + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2, kLBO2),
+                        for (int j = 0; j < tc::kK2Steps; j++)   // priors_corr += h2_lo W3_hi
+                            tc::mma_f16_ts(ts + tc::oDm + N2, ts + tc::oAl + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2, kLBO2),
                                            idesc2, 1);
                         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(&d2_full)));
                     }
@@ -417,7 +418,7 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
                         constexpr int c = decltype(cc)::value;
                         float pm_[16], pc_[16];
                         tc::tmem_ld16(slot_lane + tc::oDm + 16 * c, pm_);
-                        tc::tmem_ld16(slot_lane + tc::oDc + 16 * c, pc_);
+                        tc::tmem_ld16(slot_lane + tc::oDm + N2 + 16 * c, pc_);
                         asm volatile("tcgen05.wait::ld.sync.aligned;");
                         if (last) {
                             asm volatile("tcgen05.fence::before_thread_sync;");
@@ -478,7 +479,7 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
 
 template <int L>
 constexpr size_t tc_smem_bytes() {
-    return size_t(2) * tc::kBPieceBytes + 2 * tc::b2_piece_bytes(1 << L) +
+    return size_t(tc::kBBytes) + tc::b2_bytes(1 << L) +
            (size_t(tc::kProdWarps + tc::kConsWarps) * kTileFloats + 4 * (tc::kK / 2)) * sizeof(float) +
            (L > 5 ? SmemTrellis<L>::bytes(32 * tc::kConsWarps) : 0);
 }
