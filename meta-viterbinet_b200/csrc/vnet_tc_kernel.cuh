@@ -32,8 +32,8 @@
 
 namespace mvn {
 
-#ifndef MVN_NR_ALL
-#define MVN_NR_ALL 0
+#ifndef MVN_NR_SEL   // which pairs of a k-step take the Newton-Raphson reciprocal: 0 none, 1 every other, 2 one in four, 3 all
+#define MVN_NR_SEL 1
 #endif
 namespace tc {
 constexpr int kM = 128, kN = 64, kK = 112;    // MMA tile: frames x padded outputs x padded hidden units (+ bias column)
@@ -158,7 +158,7 @@ __device__ __forceinline__ void compute_chunk(uint32_t sP_addr, int c0, u64 yy, 
 #pragma unroll
     for (int c = 0; c < 8; c++) {
         if (!LAST || c < 2) {
-            if (MVN_NR_ALL || (c & 1)) split2_f16(sigmoid2<true>(sP_addr, 8 * c0 + c, yy), vh[c], vl[c]);
+            if (MVN_NR_SEL == 3 || (MVN_NR_SEL == 1 && (c & 1)) || (MVN_NR_SEL == 2 && (c & 3) == 3)) split2_f16(sigmoid2<true>(sP_addr, 8 * c0 + c, yy), vh[c], vl[c]);
             else split2_f16(sigmoid2<false>(sP_addr, 8 * c0 + c, yy), vh[c], vl[c]);
         } else {  // k = 100 is the bias column (1.0 = fp16 0x3C00 in the low half), k > 100 is zero padding
             vh[c] = (c == 2) ? 0x00003c00u : 0u;
@@ -261,8 +261,8 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
 #pragma unroll
         for (int s = 0; s < 2; s++) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&d_full[s])));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&slot_free[s])), "n"(32 * tc::kConsWarps));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&a_full[s])), "n"(32 * tc::kProdWarps));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&slot_free[s])), "n"(tc::kConsWarps));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&a_full[s])), "n"(tc::kProdWarps));
         }
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&d2_full)));
         asm volatile("fence.mbarrier_init.release.cluster;");
@@ -334,7 +334,8 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
                     asm volatile("tcgen05.wait::st.sync.aligned;");
                     asm volatile("tcgen05.fence::before_thread_sync;");
                     TC_TRACE(3, tid == 0);
-                    tc::mbar_arrive(smem_addr(&a_full[slot]));  // 256 arrivals release the MMA warp
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(smem_addr(&a_full[slot]));  // one arrival per producer warp
                     __syncwarp();
                 }
                 __syncwarp();
@@ -423,7 +424,8 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
                         if (last) {
                             asm volatile("tcgen05.fence::before_thread_sync;");
                             TC_TRACE(12, warp == tc::kProdWarps && lane == 0);
-                            tc::mbar_arrive(smem_addr(&slot_free[slot]));    // the slot's A and D columns may be refilled
+                            __syncwarp();
+                            if (lane == 0) tc::mbar_arrive(smem_addr(&slot_free[slot]));  // the slot's A and D columns may be refilled
                         }
                         float pr[C], cost[C];
 #pragma unroll

@@ -12,7 +12,7 @@ __device__ __forceinline__ uint64_t desc(uint32_t saddr, uint32_t lbo) {
     return uint64_t((saddr >> 4) & 0x3fff) | (uint64_t((lbo >> 4) & 0x3fff) << 16) | (uint64_t(128 >> 4) << 32) | (uint64_t(1) << 46);
 }
 
-template <int N, bool TS>
+template <int N, bool TS, int ND = 1>
 __device__ void run(uint32_t tmem, uint8_t *smem, uint64_t *bar, uint32_t &parity, long long *out) {
     const uint32_t idesc = (1u << 4) | (uint32_t(N >> 3) << 17) | (uint32_t(128 >> 4) << 24);
     const uint32_t lbo_b = (N / 8) * 128, lbo_a = (128 / 8) * 128;
@@ -26,7 +26,7 @@ __device__ void run(uint32_t tmem, uint8_t *smem, uint64_t *bar, uint32_t &parit
             const uint64_t bd = desc(sB + uint32_t(2 * (j % 7)) * lbo_b, lbo_b);
             if (TS) {
                 asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                             "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem),
+                             "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem + (j % ND) * N),
                              "r"(tmem + 256 + (j % 7) * 8), "l"(bd), "r"(idesc), "r"(1));
             } else {
                 const uint64_t ad = desc(sA + uint32_t(2 * (j % 7)) * lbo_a, lbo_a);
@@ -92,6 +92,10 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(long long *out) {
         run<64, false>(tmem, smem, &bar, parity, out + 14);
         run<128, false>(tmem, smem, &bar, parity, out + 16);
         run<256, false>(tmem, smem, &bar, parity, out + 18);
+        run<16, true, 2>(tmem, smem, &bar, parity, out + 20);
+        run<64, true, 2>(tmem, smem, &bar, parity, out + 22);
+        run<64, true, 4>(tmem, smem, &bar, parity, out + 24);
+        run<128, true, 2>(tmem, smem, &bar, parity, out + 26);
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
@@ -99,7 +103,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(long long *out) {
 }
 
 int main() {
-    long long *d, h[20];
+    long long *d, h[28];
     cudaMalloc(&d, sizeof(h));
     cudaMemset(d, 0, sizeof(h));
     const int smem = 65536 + 32768;
@@ -114,5 +118,9 @@ int main() {
             printf("%s M=128 N=%3d K=16 f16: issue %6.1f cycles/MMA, issue->complete %6.1f cycles/MMA (ideal %5.1f)\n",
                    m == 0 ? "A in TMEM" : "A in smem", Ns[i], h[(m * 5 + i) * 2] / 42.0, h[(m * 5 + i) * 2 + 1] / 42.0,
                    128.0 * Ns[i] * 16 * 2 / 8192.0);
+    const char *extra[4] = {"N= 16, 2 independent accumulators", "N= 64, 2 independent accumulators",
+                            "N= 64, 4 independent accumulators", "N=128, 2 independent accumulators"};
+    for (int i = 0; i < 4; i++)
+        printf("A in TMEM %s: issue %6.1f, issue->complete %6.1f cycles/MMA\n", extra[i], h[20 + 2 * i] / 42.0, h[21 + 2 * i] / 42.0);
     return e != cudaSuccess;
 }
