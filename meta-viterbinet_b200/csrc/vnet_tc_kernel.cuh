@@ -107,6 +107,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int *ti
         }
     }
 }
+// One thread of a converged warp.  The compiler recognises the elect.sync predicate as "a single thread": MMA
+// operands then go to uniform registers once, instead of the per-instruction ELECT / R2UR / BRA.U.ANY loop it emits
+// for an ordinary divergent branch such as `if (lane == 0)`.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -201,7 +209,14 @@ __device__ __forceinline__ void h2_to_tmem(uint32_t slot_lane) {
 #ifdef MVN_TC_TRACE
 #define TC_TRACE(ev, cond)                                                                               \
     do {                                                                                                 \
-        if (trace && blockIdx.x == 0 && (cond) && n < 64) trace[n * 16 + (ev)] = clock64();                 \
+        if (trace && blockIdx.x == 0 && (cond) && n < 64) {                                                 \
+            trace[n * 16 + (ev)] = clock64();                                                            \
+            if ((ev) == 0) {  /* wall clock next to the cycle counter: effective SM clock under this load */ \
+                unsigned long long gt;                                                                   \
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));                                    \
+                trace[n * 16 + 14] = (long long)gt;                                                      \
+            }                                                                                            \
+        }                                                                                                \
     } while (0)
 #else
 #define TC_TRACE(ev, cond) do {} while (0)
@@ -352,7 +367,7 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
                     tc::mbar_wait(smem_addr(&a_full[slot]), use & 1, timeout_flag);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     TC_TRACE(4, lane == 0);
-                    if (lane == 0) {
+                    if (tc::elect_one()) {
                         const uint32_t ts = tmem + slot * tc::kSlotCols;
 #pragma unroll
                         for (int j = 0; j < tc::kKSteps; j++)   // D_main | D_corr = A_hi [B_hi | B_lo]
@@ -395,7 +410,7 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
                     TC_TRACE(8, warp == tc::kProdWarps && lane == 0);
                     asm volatile("bar.sync 2, %0;" ::"n"(32 * tc::kConsWarps));
                     TC_TRACE(9, warp == tc::kProdWarps && lane == 0);
-                    if (warp == tc::kProdWarps && lane == 0) {       // one consumer thread issues layer 3: 4 + 4 MMAs
+                    if (warp == tc::kProdWarps && tc::elect_one()) {  // one consumer thread issues layer 3: 4 + 4 MMAs
                         asm volatile("tcgen05.fence::after_thread_sync;");
 #pragma unroll
                         for (int j = 0; j < tc::kK2Steps; j++)   // priors_main | priors_corr = h2_hi [W3_hi | W3_lo]

@@ -38,3 +38,5 @@ for a, b, label in [(0, 1, 'producer compute'), (1, 2, 'producer waits for slot'
                     (10, 11, 'layer-3 MMAs -> d2_full seen'), (11, 12, 'ld priors, release slot'), (12, 13, 'ACS'), (6, 7, 'consumer idle waiting for d_full')]:
     print(f'  {label:40s} {d(a, b):8.0f}')
 print(f'  stage period (consumer)                  {float(np.median(np.diff(t[16:56, 13]))):8.0f}')
+mhz = (t[60, 0] - t[4, 0]) / max(1, (t[60, 14] - t[4, 14])) * 1000.0
+print(f'  effective SM clock during the kernel (clock64 / globaltimer over stages 4..60): {mhz:8.0f} MHz')
