@@ -31,6 +31,24 @@ int mvn_traceback(const uint32_t *survivors, const float *final_pm, int64_t B, i
 /* Branch metrics of the full-CSI Viterbi as a tensor cost [B,T,S] (va_detector.py:62-68), for the MLSE path. */
 int mvn_va_cost(const float *y, int64_t B, int T, int L, const float *state_priors, int n_h, float *cost, void *stream);
 
+/* ---- f2: Reed-Solomon over GF(2^8), primitive polynomial 0x11d, generator roots 2^0 .. 2^(nsym-1)
+ * (ecc/rs_main.py:9-37, rs_encoder.py:7-37, rs_decoder.py:37-218).  Words are rows of bits stored as fp32 0/1 (the
+ * detectors' output format; any nonzero value counts as 1), 8 bits per byte, most significant bit first
+ * (numpy packbits, polynomials_manipulation.py:119-125).  nsym = 1..32 parity bytes, n_bytes = k_bytes + nsym <= 255.
+ *
+ * mvn_rs_decode replaces rs_main.decode per detected word (trainer.py:234-236, :298): rx_bits [B, ld_in] with
+ * 8*n_bytes used columns -> msg_bits [B, ld_out], 8*(n_bytes-nsym) columns written.  Bit-exact with the reference also
+ * beyond the code's capacity: when Berlekamp-Massey claims more than nsym/2 errors the received message bytes are
+ * returned unchanged, when the locator has fewer roots than its degree the partial correction is applied.
+ * status [B] (optional): 0 clean, 1 corrected, 2 too many errors (unchanged), 3 missing roots (partial correction).
+ *
+ * mvn_rs_encode replaces rs_main.encode (channel_dataset.py:51, trainer.py:286,304,315): msg_bits [B, ld_in] with
+ * 8*k_bytes used columns -> cw_bits [B, ld_out], 8*(k_bytes+nsym) columns: message then parity. */
+int mvn_rs_decode(const float *rx_bits, int64_t B, int ld_in, int n_bytes, int nsym, float *msg_bits, int ld_out,
+                  int32_t *status, void *stream);
+int mvn_rs_encode(const float *msg_bits, int64_t B, int ld_in, int k_bytes, int nsym, float *cw_bits, int ld_out,
+                  void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,6 +46,8 @@ _PROTOS = {
                                      c_void_p, c_void_p]),
     'mvn_traceback': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'mvn_va_cost': (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    'mvn_rs_decode': (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    'mvn_rs_encode': (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     'mvn_fp32_peak': (c_int, [c_int, c_int, POINTER(c_double), POINTER(c_double), c_void_p]),
 }
 

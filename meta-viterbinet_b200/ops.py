@@ -195,6 +195,35 @@ def channel_transmit(bits, taps, snr_db, noise=None, seed=0):
     return y
 
 
+def rs_decode(detected, nsym, return_status=False):
+    """Reed-Solomon decoding of a batch of detected words (ecc/rs_main.py:21-37 per row, trainer.py:234-236):
+    detected [B, 8*n_bytes] 0/1 -> [B, 8*(n_bytes-nsym)] fp32 0/1.  status (int32 [B]): 0 clean, 1 corrected,
+    2 too many errors (returned unchanged), 3 locator with missing roots (partial correction, as the reference)."""
+    lib = _bind_next()
+    x = dev_f32(detected)
+    if x.dim() != 2 or x.shape[1] % 8:
+        raise ValueError('detected must be [B, 8*n_bytes]')
+    B, n_bytes = x.shape[0], x.shape[1] // 8
+    k = n_bytes - int(nsym)
+    out = torch.empty((B, 8 * max(k, 0)), dtype=torch.float32, device=x.device)
+    st = torch.empty(B, dtype=torch.int32, device=x.device) if return_status else None
+    check(lib.mvn_rs_decode(ptr(x), B, x.shape[1], n_bytes, int(nsym), ptr(out), out.shape[1], ptr(st), stream()))
+    return (out, st) if return_status else out
+
+
+def rs_encode(words, nsym):
+    """Systematic Reed-Solomon encoding (ecc/rs_main.py:9-18 per row): words [B, 8*k_bytes] 0/1 ->
+    [B, 8*(k_bytes+nsym)] fp32 0/1, message bits followed by the parity bits."""
+    lib = _bind_next()
+    x = dev_f32(words)
+    if x.dim() != 2 or x.shape[1] % 8:
+        raise ValueError('words must be [B, 8*k_bytes]')
+    B, k = x.shape[0], x.shape[1] // 8
+    out = torch.empty((B, 8 * (k + int(nsym))), dtype=torch.float32, device=x.device)
+    check(lib.mvn_rs_encode(ptr(x), B, x.shape[1], k, int(nsym), ptr(out), out.shape[1], stream()))
+    return out
+
+
 def mlse_decode(cost, n_stages=None, terminated=False, out_format=OUT_F32):
     """True-MLSE decoding of cost [B,T,S] by survivor traceback (the mode SURVEY.md §8f ranks 3rd; the reference's own
     rule is acs_decode).  terminated=True starts the traceback from state 0 (zero-padded words), else from the best

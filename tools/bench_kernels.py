@@ -61,3 +61,26 @@ for L in range(3, 9):
     ms = timeit(lambda: mvn.ops.vnet_decode(y[:fr], w), reps=3)
     flop = 2 * (100 + 5000 + 50 * S) + 2 * S
     print(f'VNET L={L} frames={fr}: {ms:8.3f} ms  {fr * T / ms / 1e6:8.3f} Gsym/s  {flop * fr * T / ms / 1e9:7.2f} TFLOP/s', flush=True)
+
+# Reed-Solomon (f2): words/s and HBM bytes (fp32 bit rows in and out), clean words and words with nsym/2 byte errors
+import numpy as np
+for k_bytes, nsym, n_words in ((15, 2, 1 << 20), (60, 8, 1 << 19), (223, 32, 1 << 17)):
+    n = k_bytes + nsym
+    g = torch.Generator(device='cpu').manual_seed(k_bytes)
+    msg = torch.randint(0, 2, (n_words, 8 * k_bytes), generator=g).float().to(dev)
+    ms = timeit(lambda: mvn.ops.rs_encode(msg, nsym), reps=3)
+    cw = mvn.ops.rs_encode(msg, nsym)
+    print(f'RS   encode k={k_bytes} nsym={nsym} words={n_words}: {ms:8.3f} ms  {n_words / ms / 1e3:8.2f} Mwords/s  '
+          f'{4 * 8 * (k_bytes + n) * n_words / ms / 1e6:8.1f} GB/s', flush=True)
+    for label, n_bad in (('clean', 0), (f'{nsym // 2} byte errors', nsym // 2)):
+        rx = cw.clone()
+        if n_bad:
+            pos = torch.stack([torch.randperm(n, generator=g)[:n_bad] for _ in range(4096)]).to(dev)   # pattern pool
+            pos = pos[torch.arange(n_words, device=dev) % 4096]
+            rows = torch.arange(n_words, device=dev).unsqueeze(1).expand_as(pos)
+            rx[rows, 8 * pos + 3] = 1 - rx[rows, 8 * pos + 3]
+        ms = timeit(lambda: mvn.ops.rs_decode(rx, nsym), reps=3)
+        ok = bool((mvn.ops.rs_decode(rx, nsym) == msg).all())
+        print(f'RS   decode k={k_bytes} nsym={nsym} {label:>15s}: {ms:8.3f} ms  {n_words / ms / 1e3:8.2f} Mwords/s  '
+              f'{4 * 8 * (k_bytes + n) * n_words / ms / 1e6:8.1f} GB/s  recovered={ok}', flush=True)
+    del msg, cw, rx
