@@ -299,7 +299,7 @@ static int launch_variant(VnetParams p, cudaStream_t st) {
 
 __device__ int g_tc_timeout = 0;
 #ifdef MVN_TC_TRACE
-__device__ long long g_tc_trace[64 * 16];
+__device__ long long g_tc_trace[64 * 32];
 #endif
 
 // tcgen05 variant (memory_length <= 6): every CTA stages its own weights (W2/b2 as bf16 pieces, the rest fp32).
@@ -459,6 +459,6 @@ extern "C" int mvn_debug_tc_timeout(void) {
 
 #ifdef MVN_TC_TRACE
 extern "C" int mvn_debug_tc_trace(long long *host_out) {
-    return int(cudaMemcpyFromSymbol(host_out, mvn::g_tc_trace, sizeof(long long) * 64 * 16));
+    return int(cudaMemcpyFromSymbol(host_out, mvn::g_tc_trace, sizeof(long long) * 64 * 32));
 }
 #endif

@@ -9,7 +9,10 @@
 // exact in fp32 and the 2^11 scaling keeps the remainders normal.  On the reference's fixtures the priors are
 // 2.4e-7 of the row maximum away from fp64 — closer than a plain fp32 dot product (4.4e-7), see DESIGN.md §5.1.
 // (A first version used an exact three-way bf16 split with six chains: same accuracy, twice the tensor work.)
-// The bias b2 rides along as column k=100 of B against a constant-1 column of A.
+// The bias b2 rides along as column k=100 of B against a constant column of A.
+// Layer 2 takes its A operand PRE-SCALED: the producers compute g = 2048 h1 directly (see denom2), so the remainder
+// g - fp16(g) is a normal fp16 number without a scaling multiply and goes to D_main; D_main + D_corr / 2048 is then
+// 2048 (W2 h1 + b2), which is what the ReLU / split of layer 3 wants as input.
 //
 // Warp-specialised pipeline over a two-slot TMEM ring; one frame = one TMEM lane, 128 frames per CTA tile:
 //   8 producer warps : y -> 100 sigmoids -> fp16 hi/lo split -> tcgen05.st  A_hi, A_lo [128 x 112] (2 x 56 columns)
@@ -32,9 +35,6 @@
 
 namespace mvn {
 
-#ifndef MVN_NR_SEL   // which pairs of a k-step take the Newton-Raphson reciprocal: 0 none, 1 every other, 2 one in four, 3 all
-#define MVN_NR_SEL 1
-#endif
 namespace tc {
 constexpr int kM = 128, kN = 64, kK = 112;    // MMA tile: frames x padded outputs x padded hidden units (+ bias column)
 constexpr int kKSteps = kK / 16;              // UMMA_K = 16 for fp16
@@ -92,16 +92,19 @@ __device__ __forceinline__ void tmem_ld2(uint32_t addr, float *r) {
     r[0] = __uint_as_float(u0);
     r[1] = __uint_as_float(u1);
 }
+// try_wait with a suspend-time hint: the waiting warp is parked by the hardware until the phase completes (or the
+// hint expires) instead of spinning.  A spinning warp competes for the issue slots of its scheduler; the MMA warp
+// waits most of the time and made the producers that share its scheduler the slowest of the CTA (pipeline trace).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int *timeout_flag) {
     uint32_t done = 0;
     int spins = 0;
     while (!done) {
         asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
             : "=r"(done)
-            : "r"(bar), "r"(parity)
+            : "r"(bar), "r"(parity), "r"(0x989680)
             : "memory");
-        if (!done && ++spins > (1 << 22)) {  // never expected; keeps a bug from hanging the GPU
+        if (!done && ++spins > (1 << 16)) {  // never expected; keeps a bug from hanging the GPU
             if (timeout_flag) *timeout_flag = 1;
             break;
         }
@@ -120,42 +123,51 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 
 // ---- producer math on fp32x2 pairs of hidden units (k, k+1) --------------------------------------
-// staged pair table: sP[k/2] = (w1'[k], w1'[k+1], b1'[k], b1'[k+1]) with w1' = -log2(e) w1 (one LDS.128)
-// The producers are bound by the XU (MUFU) pipe: 16 lanes per clock per SM, and EX2 + RCP for 100 hidden units is
-// 200 MUFU per symbol (pipeline trace: profiles/r01_tc_pipeline_trace_v4.txt).  NR = true computes the reciprocal on
-// the idle FMA pipe instead: bit-trick seed (|err| < 12.5 %) and three Newton steps r += r (1 - d r) on packed
-// pairs (6e-8 after the third); the callers alternate the two forms to balance XU and issue slots.
-template <bool NR>
-__device__ __forceinline__ u64 sigmoid2(uint32_t sP_addr, int pair, u64 yy) {
+// staged pair table: sP[k/2] = (w1'[k], w1'[k+1], b1'[k], b1'[k+1]) with w1' = -log2(e) w1, b1' = -log2(e) b1 - 11
+// (one LDS.128), so that 2^(w1' y + b1') = e^-a / 2048 and the reciprocal of  d' = e^-a / 2048 + 2^-11  is
+// g = 2048 sigmoid(a): the hidden activations are produced PRE-SCALED by 2^11.  Then the fp16 remainder g - fp16(g)
+// (< 1) needs no scaling of its own, it accumulates into D_main next to the hi piece, and the consumer's
+// x = D_main + D_corr / 2048 is 2048 (W2 h1 + b2), exactly the scaled value its own split wants.
+// The producers are bound by issue slots and by the XU (MUFU) pipe (16 lanes per clock per SM; pipeline trace in
+// profiles/): EX2 + RCP per unit is 200 MUFU per symbol.  Four reciprocals share ONE MUFU.RCP (Montgomery's trick:
+// 1/a = b c d / (a b c d), arranged on packed pairs so that it costs 7 instructions per four values); the exponent
+// is clamped so that the product of four d' stays finite (sigmoid floor 2^-41, far below fp32 resolution of the sums).
+__device__ __forceinline__ u64 denom2(uint32_t sP_addr, int pair, u64 yy) {
     u64 w, b;
     lds128(sP_addr + 16 * pair, w, b);
     float x0, x1;
     unpack2(fma2(yy, w, b), x0, x1);
-    if (!NR) {
-        float d0, d1;
-        unpack2(add2(pack2(ex2_approx(x0), ex2_approx(x1)), 0x3f8000003f800000ull), d0, d1);
-        return pack2(rcp_approx(d0), rcp_approx(d1));
-    } else {
-        // clamp the exponent so that d = 1 + 2^x stays finite (sigmoid < 2^-80 is 0 to every later digit)
-        const u64 d = add2(pack2(ex2_approx(fminf(x0, 80.f)), ex2_approx(fminf(x1, 80.f))), 0x3f8000003f800000ull);
-        float d0, d1;
-        unpack2(d, d0, d1);
-        u64 r = pack2(__uint_as_float(0x7ef311c7u - __float_as_uint(d0)), __uint_as_float(0x7ef311c7u - __float_as_uint(d1)));
-        const u64 nd = d ^ 0x8000000080000000ull;
-#pragma unroll
-        for (int it = 0; it < 3; it++) r = fma2(r, fma2(nd, r, 0x3f8000003f800000ull), r);
-        return r;
-    }
+    return add2(pack2(ex2_approx(fminf(x0, 30.f)), ex2_approx(fminf(x1, 30.f))), 0x3a0000003a000000ull);  // + 2^-11
 }
-// (h_k, h_{k+1}) -> fp16x2 words of the hi pieces and of the scaled remainders (low half = even k)
-__device__ __forceinline__ void split2_f16(u64 h, uint32_t &whi, uint32_t &wlo) {
+// (1/p.x, 1/p.y) and (1/q.x, 1/q.y) from one reciprocal
+__device__ __forceinline__ void recip4(u64 p, u64 q, u64 &rp, u64 &rq) {
+    float m0, m1;
+    unpack2(mul2(p, q), m0, m1);                   // (p.x q.x, p.y q.y)
+    const float r = rcp_approx(m0 * m1);
+    const u64 inv = pack2(r * m1, r * m0);         // (1 / (p.x q.x), 1 / (p.y q.y))
+    rp = mul2(inv, q);
+    rq = mul2(inv, p);
+}
+// (g_k, g_{k+1}) -> fp16x2 words of the hi pieces and of the (unscaled) remainders (low half = even k)
+__device__ __forceinline__ void split2_pre(u64 g, uint32_t &whi, uint32_t &wlo) {
+    float g0, g1;
+    unpack2(g, g0, g1);
+    const __half2 hi = __floats2half2_rn(g0, g1);
+    const float2 f = __half22float2(hi);
+    float r0, r1;
+    unpack2(fma2(pack2(f.x, f.y), 0xbf800000bf800000ull, g), r0, r1);   // g - f, exact
+    const __half2 lo = __floats2half2_rn(r0, r1);
+    whi = *reinterpret_cast<const uint32_t *>(&hi);
+    wlo = *reinterpret_cast<const uint32_t *>(&lo);
+}
+// X = 2048 h (consumer side) -> fp16x2 words of hi = fp16(h) and lo = fp16((h - hi) 2048): the A operand of layer 3
+__device__ __forceinline__ void split2_f16(u64 X, uint32_t &whi, uint32_t &wlo) {
     float h0, h1;
-    unpack2(h, h0, h1);
+    unpack2(mul2(X, 0x3a0000003a000000ull), h0, h1);   // h = X / 2048
     const __half2 hi = __floats2half2_rn(h0, h1);
     const float2 f = __half22float2(hi);
-    // (h - f) * 2048 on both halves: f * (-2048) + h * 2048, every step exact except the final fp16 rounding
     float r0, r1;
-    unpack2(fma2(pack2(f.x, f.y), 0xc5000000c5000000ull, mul2(h, 0x4500000045000000ull)), r0, r1);
+    unpack2(fma2(pack2(f.x, f.y), 0xc5000000c5000000ull, X), r0, r1);   // X - 2048 f, exact up to the final rounding
     const __half2 lo = __floats2half2_rn(r0, r1);
     whi = *reinterpret_cast<const uint32_t *>(&hi);
     wlo = *reinterpret_cast<const uint32_t *>(&lo);
@@ -164,13 +176,16 @@ __device__ __forceinline__ void split2_f16(u64 h, uint32_t &whi, uint32_t &wlo) 
 template <bool LAST>
 __device__ __forceinline__ void compute_chunk(uint32_t sP_addr, int c0, u64 yy, uint32_t (&vh)[8], uint32_t (&vl)[8]) {
 #pragma unroll
-    for (int c = 0; c < 8; c++) {
+    for (int c = 0; c < 8; c += 2) {
         if (!LAST || c < 2) {
-            if (MVN_NR_SEL == 3 || (MVN_NR_SEL == 1 && (c & 1)) || (MVN_NR_SEL == 2 && (c & 3) == 3)) split2_f16(sigmoid2<true>(sP_addr, 8 * c0 + c, yy), vh[c], vl[c]);
-            else split2_f16(sigmoid2<false>(sP_addr, 8 * c0 + c, yy), vh[c], vl[c]);
-        } else {  // k = 100 is the bias column (1.0 = fp16 0x3C00 in the low half), k > 100 is zero padding
-            vh[c] = (c == 2) ? 0x00003c00u : 0u;
-            vl[c] = 0u;
+            u64 g0, g1;
+            recip4(denom2(sP_addr, 8 * c0 + c, yy), denom2(sP_addr, 8 * c0 + c + 1, yy), g0, g1);
+            split2_pre(g0, vh[c], vl[c]);
+            split2_pre(g1, vh[c + 1], vl[c + 1]);
+        } else {  // k = 100 is the bias column (2048 = fp16 0x6800 in the low half), k > 100 is zero padding
+            vh[c] = (c == 2) ? 0x00006800u : 0u;
+            vh[c + 1] = 0u;
+            vl[c] = vl[c + 1] = 0u;
         }
     }
 }
@@ -189,9 +204,10 @@ __device__ __forceinline__ void h2_to_tmem(uint32_t slot_lane) {
         for (int q = 0; q < 8; q++) {
             const int k = 16 * c0 + 2 * q;
             if (k + 1 < kH2) {
-                const float h0 = fmaxf(fmaf(c[2 * q], kInvScale, m[2 * q]), 0.f);
-                const float h1 = fmaxf(fmaf(c[2 * q + 1], kInvScale, m[2 * q + 1]), 0.f);
-                split2_f16(pack2(h0, h1), vh[q], vl[q]);
+                // D_main + D_corr / 2048 = 2048 (W2 h1 + b2): ReLU keeps the scale, split2_f16 takes the scaled value
+                const float x0 = fmaxf(fmaf(c[2 * q], kInvScale, m[2 * q]), 0.f);
+                const float x1 = fmaxf(fmaf(c[2 * q + 1], kInvScale, m[2 * q + 1]), 0.f);
+                split2_f16(pack2(x0, x1), vh[q], vl[q]);
             } else {  // k2 = 50: bias column (1.0 in the low half); beyond: zero padding
                 vh[q] = (k == kH2) ? 0x00003c00u : 0u;
                 vl[q] = 0u;
@@ -205,16 +221,16 @@ __device__ __forceinline__ void h2_to_tmem(uint32_t slot_lane) {
 }  // namespace tc
 
 // Optional pipeline trace (debug builds only, -DMVN_TC_TRACE): CTA 0 records clock64() at the key points of the
-// first 64 stages, 16 events per stage, into trace[stage*16 + event].
+// first 64 stages, 32 event slots per stage, into trace[stage*32 + event]; slots 16+w / 24+w: start / stored of producer warp w.
 #ifdef MVN_TC_TRACE
 #define TC_TRACE(ev, cond)                                                                               \
     do {                                                                                                 \
         if (trace && blockIdx.x == 0 && (cond) && n < 64) {                                                 \
-            trace[n * 16 + (ev)] = clock64();                                                            \
+            trace[n * 32 + (ev)] = clock64();                                                            \
             if ((ev) == 0) {  /* wall clock next to the cycle counter: effective SM clock under this load */ \
                 unsigned long long gt;                                                                   \
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));                                    \
-                trace[n * 16 + 14] = (long long)gt;                                                      \
+                trace[n * 32 + 14] = (long long)gt;                                                      \
             }                                                                                            \
         }                                                                                                \
     } while (0)
@@ -258,8 +274,8 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
         const int k = 2 * i;
         sP[4 * i + 0] = k < kH1 ? p.w.w1[k] * kNegLog2e : 0.f;
         sP[4 * i + 1] = k + 1 < kH1 ? p.w.w1[k + 1] * kNegLog2e : 0.f;
-        sP[4 * i + 2] = k < kH1 ? p.w.b1[k] * kNegLog2e : 0.f;
-        sP[4 * i + 3] = k + 1 < kH1 ? p.w.b1[k + 1] * kNegLog2e : 0.f;
+        sP[4 * i + 2] = k < kH1 ? fmaf(p.w.b1[k], kNegLog2e, -11.f) : 0.f;      // 2^(...) = e^-a / 2048
+        sP[4 * i + 3] = k + 1 < kH1 ? fmaf(p.w.b1[k + 1], kNegLog2e, -11.f) : 0.f;
     }
     // ---- W3 (and b3 as column k2=50) -> fp16 pieces, canonical K-major layout with N2 rows (states)
     for (int idx = tid; idx < N2 * tc::kK2; idx += tc::kThreadsTc) {
@@ -322,6 +338,7 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
                     // Compute this stage's pieces into registers BEFORE waiting for the slot: the sigmoid/split work
                     // then overlaps the MMAs and the consumer of the stage that still owns the slot.
                     TC_TRACE(0, tid == 0);
+                    TC_TRACE(24 + warp, lane == 0);
                     // k-steps per producer warp: warps 0-3 take steps 0..2 (24 pairs of hidden units), warps 4-7 take
                     // steps 3..6 (26 pairs + the bias/padding columns), so both halves finish together
                     constexpr int NKS = 4;
@@ -349,6 +366,7 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
                     asm volatile("tcgen05.wait::st.sync.aligned;");
                     asm volatile("tcgen05.fence::before_thread_sync;");
                     TC_TRACE(3, tid == 0);
+                    TC_TRACE(16 + warp, lane == 0);
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(smem_addr(&a_full[slot]));  // one arrival per producer warp
                     __syncwarp();
@@ -374,8 +392,8 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
                             tc::mma_f16_ts(ts + tc::oDm, ts + tc::oAh + j * 8, tc::b_desc(sB_addr + uint32_t(2 * j) * tc::kLBO), idescw,
                                            j > 0);
 #pragma unroll
-                        for (int j = 0; j < tc::kKSteps; j++)   // D_corr += A_lo B_hi
-                            tc::mma_f16_ts(ts + tc::oDc, ts + tc::oAl + j * 8, tc::b_desc(sB_addr + uint32_t(2 * j) * tc::kLBO), idesc, 1);
+                        for (int j = 0; j < tc::kKSteps; j++)   // D_main += A_lo B_hi (the remainder of the pre-scaled A is unscaled)
+                            tc::mma_f16_ts(ts + tc::oDm, ts + tc::oAl + j * 8, tc::b_desc(sB_addr + uint32_t(2 * j) * tc::kLBO), idesc, 1);
                         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                             smem_addr(&d_full[slot])));
                     }
@@ -410,7 +428,7 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
                     TC_TRACE(8, warp == tc::kProdWarps && lane == 0);
                     asm volatile("bar.sync 2, %0;" ::"n"(32 * tc::kConsWarps));
                     TC_TRACE(9, warp == tc::kProdWarps && lane == 0);
-                    if (warp == tc::kProdWarps && tc::elect_one()) {  // one consumer thread issues layer 3: 4 + 4 MMAs
+                    if (warp == tc::kProdWarps + 1 && tc::elect_one()) {  // one consumer thread (not on the MMA warp's scheduler) issues layer 3: 4 + 4 MMAs
                         asm volatile("tcgen05.fence::after_thread_sync;");
 #pragma unroll
                         for (int j = 0; j < tc::kK2Steps; j++)   // priors_main | priors_corr = h2_hi [W3_hi | W3_lo]

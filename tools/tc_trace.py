@@ -21,9 +21,9 @@ for _ in range(2):
     mvn.ops.vnet_decode(y, w)
 torch.cuda.synchronize()
 lib = _lib.load()
-buf = (ctypes.c_longlong * (64 * 16))()
+buf = (ctypes.c_longlong * (64 * 32))()
 lib.mvn_debug_tc_trace(buf)
-t = np.array(buf[:]).reshape(64, 16)
+t = np.array(buf[:]).reshape(64, 32)
 names = ['P start', 'P computed', 'P slot acquired', 'P stored', 'M a_full seen', 'M issued', 'C wait d_full', 'C d_full seen',
          'C h2->tmem done', 'C barrier passed', 'C mma2 issued', 'C d2_full seen', 'C slot released', 'C acs done']
 base = t[8, 0]
@@ -40,3 +40,6 @@ for a, b, label in [(0, 1, 'producer compute'), (1, 2, 'producer waits for slot'
 print(f'  stage period (consumer)                  {float(np.median(np.diff(t[16:56, 13]))):8.0f}')
 mhz = (t[60, 0] - t[4, 0]) / max(1, (t[60, 14] - t[4, 14])) * 1000.0
 print(f'  effective SM clock during the kernel (clock64 / globaltimer over stages 4..60): {mhz:8.0f} MHz')
+print('  per producer warp, median over stages 16..55 (cycles): start -> stored | stored relative to warp 0')
+for w in range(8):
+    print(f'    warp {w}: {float(np.median(t[16:56, 16 + w] - t[16:56, 24 + w])):8.0f} | {float(np.median(t[16:56, 16 + w] - t[16:56, 16])):8.0f}')
