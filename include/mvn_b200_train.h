@@ -63,6 +63,13 @@ int mvn_vnet_priors_backward2(const float *y, int64_t N, int L, const float *the
                               const float *u, float *grad_theta2, float *grad_grad_priors, void *workspace,
                               void *stream);
 
+/* ---- detection with per-realisation weights: VNETDetector.forward(y, 'val') (vnet_detector.py:46-61) for R
+ * independent runs at once, run r using theta[r] on its own word y[r] — the shape of the word-by-word online
+ * evaluation (trainer.py:267-298), where every run's weights differ and change between blocks.
+ * theta [R,P], y [R,T], decoded [R,T] fp32 0/1 (columns >= n_stages are 0), priors_out [R,T,S] optional. */
+int mvn_vnet_detect_batched(const float *theta, int R, int L, const float *y, int T, int n_stages, float *decoded,
+                            float *priors_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

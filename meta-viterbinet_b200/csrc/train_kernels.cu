@@ -424,6 +424,100 @@ __global__ void __launch_bounds__(kTrainThreads, 1) priors_backward2_kernel(cons
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Detection with PER-REALISATION weights (the eval_by_word shape, trainer.py:267-298: one word per call and weights
+// that change between calls).  One CTA per realisation: thread per symbol evaluates the priors with that realisation's
+// theta (blocks of 256 symbols into shared memory), then one thread runs the reference's ACS / decision recursion on
+// its register trellis — the same RegTrellis code as the batch kernels, so decisions are bit-exact functions of the
+// priors this kernel computes (and optionally exports).
+// ---------------------------------------------------------------------------------------------
+template <int L>
+__global__ void __launch_bounds__(kTrainThreads, 1) detect_batched_kernel(const float *__restrict__ theta_all, int R,
+                                                                         const float *__restrict__ y, int T, int n_stages,
+                                                                         float *__restrict__ decoded,
+                                                                         float *__restrict__ priors_out) {
+    constexpr int S = 1 << L;
+    using TV = ThetaView<S>;
+    using D = TrellisDims<L>;
+    constexpr int P = TV::P, PP = (P + 3) / 4 * 4, C = D::C;
+    extern __shared__ __align__(16) float sm[];
+    float *th = sm, *pri = sm + PP;  // pri[256][S]
+    for (int r = blockIdx.x; r < R; r += gridDim.x) {
+        for (int i = threadIdx.x; i < P; i += kTrainThreads) th[i] = theta_all[size_t(r) * P + i];
+        __syncthreads();
+        RegTrellis<L> tr;
+        tr.reset();
+        for (int base = 0; base < T; base += kTrainThreads) {
+            const int t = base + threadIdx.x;
+            if (t < n_stages) {
+                const float yv = y[size_t(r) * T + t];
+                float h1[kH1];
+#pragma unroll
+                for (int k = 0; k < kH1; k++) h1[k] = sigmoidf_acc(fmaf(th[TV::w1 + k], yv, th[TV::b1 + k]));
+                float z[S];
+#pragma unroll
+                for (int s = 0; s < S; s++) z[s] = th[TV::b3 + s];
+#pragma unroll 1
+                for (int o = 0; o < kH2; o++) {
+                    const float *w2 = th + TV::w2 + o * kH1;
+                    float a0 = th[TV::b2 + o], a1 = 0.f;
+#pragma unroll
+                    for (int k = 0; k < kH1; k += 2) {
+                        a0 = fmaf(w2[k], h1[k], a0);
+                        a1 = fmaf(w2[k + 1], h1[k + 1], a1);
+                    }
+                    const float h2 = fmaxf(a0 + a1, 0.f);
+#pragma unroll
+                    for (int s = 0; s < S; s++) z[s] = fmaf(th[TV::w3 + s * kH2 + o], h2, z[s]);
+                }
+#pragma unroll
+                for (int s = 0; s < S; s++) {
+                    pri[threadIdx.x * S + s] = z[s];
+                    if (priors_out) priors_out[(size_t(r) * T + t) * S + s] = z[s];
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const int t_end = min(kTrainThreads, n_stages - base);
+                for (int tt = 0; tt < t_end; tt++) {
+                    decoded[size_t(r) * T + base + tt] = float(tr.decide());   // before this stage's ACS (vnet_detector.py:55-61)
+                    float cost[C];
+                    if constexpr (D::NCH == 1) {
+#pragma unroll
+                        for (int i = 0; i < C; i++) cost[i] = -pri[tt * S + i];
+                        tr.template step_chunk<0>(cost);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < C; i++) cost[i] = -pri[tt * S + i];
+                        tr.template step_chunk<0>(cost);
+#pragma unroll
+                        for (int i = 0; i < C; i++) cost[i] = -pri[tt * S + C + i];
+                        tr.template step_chunk<1>(cost);
+                    }
+                    tr.commit();
+                }
+            }
+            __syncthreads();
+        }
+        for (int t = max(n_stages, 0) + threadIdx.x; t < T; t += kTrainThreads) decoded[size_t(r) * T + t] = 0.f;
+        __syncthreads();
+    }
+}
+
+template <int L>
+static int launch_detect_batched(const float *theta, int R, const float *y, int T, int n_stages, float *decoded, float *priors,
+                                 cudaStream_t st) {
+    constexpr int S = 1 << L;
+    constexpr int P = ThetaView<S>::P;
+    const size_t smem = (size_t((P + 3) / 4 * 4) + size_t(kTrainThreads) * S) * sizeof(float);
+    auto kern = detect_batched_kernel<L>;
+    MVN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    kern<<<std::max(1, std::min(R, 2 * sm_count())), kTrainThreads, smem, st>>>(theta, R, y, T, n_stages, decoded, priors);
+    note_launch();
+    MVN_CUDA(cudaGetLastError());
+    return MVN_OK;
+}
+
 static int train_grid(int R) { return std::max(1, std::min(R, 2 * sm_count())); }
 
 template <int S>
@@ -575,4 +669,15 @@ extern "C" int mvn_vnet_priors_backward2(const float *y, int64_t N, int L, const
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     MVN_TRAIN_DISPATCH(L, launch_priors_bwd2, y, N, theta, grad_priors, u, grad_theta2, grad_grad_priors,
                        static_cast<float *>(workspace), st)
+}
+
+extern "C" int mvn_vnet_detect_batched(const float *theta, int R, int L, const float *y, int T, int n_stages, float *decoded,
+                                       float *priors_out, void *stream) {
+    if (R < 0 || T < 0 || n_stages < 0 || n_stages > T || (R > 0 && T > 0 && (!theta || !y || !decoded))) {
+        set_error("mvn_vnet_detect_batched: bad argument (n_stages must be 0..T)");
+        return MVN_ERR_ARG;
+    }
+    if (R == 0 || T == 0) return MVN_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MVN_TRAIN_DISPATCH(L, launch_detect_batched, theta, R, y, T, n_stages, decoded, priors_out, st)
 }

@@ -31,6 +31,7 @@ _PROTOS = {
     'mvn_priors_backward_workspace_bytes': (c_int64, [c_int, c_int64]),
     'mvn_vnet_priors_backward': (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'mvn_vnet_priors_backward2': (c_int, [c_void_p, c_int64, c_int] + [c_void_p] * 7),
+    'mvn_vnet_detect_batched': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
 }
 _lib._PROTOS.update(_PROTOS)
 if _lib._lib is not None:          # library already loaded: bind the extra prototypes now
@@ -110,6 +111,17 @@ class BatchedVNetTrainer:
                                             ptr(self.adam_step), self.R, self.L, ptr(y), ptr(lab), y.shape[1], self.lr,
                                             ptr(loss), ptr(grad), ptr(self.workspace), stream()))
         return (loss, grad) if return_grad else loss
+
+    def detect(self, y, n_stages=None, return_priors=False):
+        """VNETDetector.forward(y, 'val') for every realisation with ITS OWN current weights, one launch.
+        y [R, T] -> decoded [R, T] fp32 0/1 (and the priors [R, T, S] the decisions were taken on)."""
+        y = dev_f32(y).reshape(self.R, -1)
+        T = y.shape[1]
+        n = T if n_stages is None else int(n_stages)
+        dec = torch.empty((self.R, T), dtype=torch.float32, device=y.device)
+        pri = torch.empty((self.R, T, 1 << self.L), dtype=torch.float32, device=y.device) if return_priors else None
+        check(load().mvn_vnet_detect_batched(ptr(self.theta), self.R, self.L, ptr(y), T, n, ptr(dec), ptr(pri), stream()))
+        return (dec, pri) if return_priors else dec
 
     def meta_step(self, y_s, tx_s, y_q, tx_q, second_order=True, update=True, return_grad=False):
         """One meta_train_loop step per realisation.  Support [R, Ns], query [R, Nq].  Returns query loss [R]."""

@@ -202,6 +202,33 @@ def test_double_backward_matches_torch(mvn, L):
         assert np.max(np.abs(a - r)) < 5e-5 * np.max(np.abs(r)) + 1e-8, (np.max(np.abs(a - r)), np.max(np.abs(r)))
 
 
+@pytest.mark.parametrize('L,T,n_stages', [(4, 136, 136), (4, 300, 290), (2, 40, 33), (5, 70, 70), (1, 9, 8)])
+def test_batched_detection_with_per_realisation_weights(mvn, L, T, n_stages):
+    """tr.detect(): every realisation decodes its word with its own weights in one launch; decisions are the
+    reference recursion on the priors the kernel computed (bit-exact), priors within 1e-5 of fp64."""
+    S, R = 1 << L, 7
+    rng = np.random.RandomState(L * 100 + T)
+    ws = [[(rng.randn(*s) * sc).astype(np.float32) for s, sc in
+           [((100, 1), 0.8), ((100,), 0.5), ((50, 100), 0.15), ((50,), 0.1), ((S, 50), 0.3), ((S,), 0.1)]] for _ in range(R)]
+    y = (rng.randn(R, T) * 1.5).astype(np.float32)
+    tr = mvn.BatchedVNetTrainer(cu(np.stack([pack(w) for w in ws])), L)
+    dec, pri = tr.detect(cu(y), n_stages=n_stages, return_priors=True)
+    dec, pri = dec.cpu().numpy(), pri.cpu().numpy()
+    assert np.all(dec[:, n_stages:] == 0)
+    for r in range(R):
+        exact = orc.vnet_priors(y[r:r + 1], ws[r], dtype=np.float64)[0]
+        err = np.abs(pri[r, :n_stages] - exact[:n_stages]) / np.abs(exact[:n_stages]).max(axis=-1, keepdims=True)
+        assert err.max() < 1e-5
+        ref, _ = orc.vnet_decode_from_priors(pri[r:r + 1], n_stages)
+        assert np.array_equal(dec[r:r + 1], ref)
+        # the batch kernel with the same weights agrees except on near-ties (different fp32 summation order)
+        one = mvn.ops.vnet_decode(cu(y[r:r + 1]), [cu(a) for a in ws[r]], n_stages=n_stages).cpu().numpy()
+        assert (one != dec[r:r + 1]).sum() <= 1
+    assert np.array_equal(tr.detect(cu(y), n_stages=n_stages).cpu().numpy(), dec)
+    with pytest.raises(mvn.MVNError):
+        tr.detect(cu(y), n_stages=T + 1)
+
+
 def test_training_rejects_unsupported_trellis(mvn):
     with pytest.raises(mvn.MVNError):
         mvn.BatchedVNetTrainer(torch.zeros(1, mvn.train.param_count(7)).cuda(), 7)
