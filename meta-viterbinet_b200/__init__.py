@@ -6,6 +6,8 @@ directory, whose name contains a '-').
 from . import _lib, ops
 from . import train
 from . import sweep
+from . import online
+from . import ecc
 from ._lib import MVNError, OUT_BITS, OUT_F32
 from .train import BatchedVNetTrainer
 from .detectors import META_VNETDetector, VADetector, VNETDetector
@@ -13,4 +15,4 @@ from .utils.metrics import calculate_error_rates
 from .utils.trellis_utils import acs_block, calculate_states, create_transition_table
 
 __all__ = ['VADetector', 'VNETDetector', 'META_VNETDetector', 'acs_block', 'calculate_states',
-           'create_transition_table', 'calculate_error_rates', 'BatchedVNetTrainer', 'train', 'sweep', 'ops', 'MVNError', 'OUT_F32', 'OUT_BITS']
+           'create_transition_table', 'calculate_error_rates', 'BatchedVNetTrainer', 'train', 'sweep', 'online', 'ecc', 'ops', 'MVNError', 'OUT_F32', 'OUT_BITS']
