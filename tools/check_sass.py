@@ -46,6 +46,19 @@ def main():
         print(f'L={L} NT={nt}: loop {len(loop)} instrs, FFMA2 {c["FFMA2"]}, LDCU {c["LDCU"]}, LDC {c["LDC"]}, '
               f'MOV {c["MOV"] + c["IMAD"]} -> {"ok" if good else "FALLBACK TO LDC"}')
         ok &= good
+    # tcgen05 kernel (default for L <= 6): tensor-core and TMEM instructions present, MMAs issued back to back
+    # (elect.sync form: no per-MMA ELECT / R2UR / BRA.U.ANY serialisation loop)
+    for L in range(1, 7):
+        body = next((f for f in funcs if f.startswith(f'_ZN3mvn21vnet_decode_tc_kernelILi{L}E')), None)
+        if body is None:
+            print(f'tcgen05 L={L}: kernel not found')
+            ok = False
+            continue
+        c = collections.Counter(m.group(1) for m in re.finditer(r'/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)', body))
+        good = c['UTCHMMA'] >= 22 and c['LDTM'] > 0 and c['STTM'] > 0 and c['UTCBAR'] >= 2 and 'BRA.U.ANY' not in body
+        print(f'tcgen05 L={L}: UTCHMMA {c["UTCHMMA"]}, LDTM {c["LDTM"]}, STTM {c["STTM"]}, UTCBAR {c["UTCBAR"]}, '
+              f'FFMA2 {c["FFMA2"]}, MUFU {c["MUFU"]}, serialised-issue loops {body.count("BRA.U.ANY")} -> {"ok" if good else "CHECK"}')
+        ok &= good
     return 0 if ok else 1
 
 
