@@ -49,7 +49,7 @@ constexpr float kScale = 2048.f, kInvScale = 1.f / 2048.f;
 constexpr uint32_t kLBO = (2 * kN / 8) * 128; // bytes between consecutive 16-byte K chunks (k-chunk stride)
 constexpr uint32_t kSBO = 128;                // bytes between 8-row groups along N
 constexpr int kBBytes = (kK / 8) * (2 * kN / 8) * 128;
-constexpr int kProdWarps = 8, kConsWarps = 4, kThreadsTc = 32 * (kProdWarps + kConsWarps + 1);  // + one MMA-issue warp
+constexpr int kProdWarps = 12, kConsWarps = 4, kThreadsTc = 32 * (kProdWarps + kConsWarps + 1);  // + one MMA-issue warp
 // layer 3 on the tensor core as well: D2[128 x 16] = h2[128 x 64] W3^T, K2 = 50 hidden units + bias column, padded
 // (N2 = max(16, n_states) output columns, so up to 64 states fit the slot's 64-column D regions)
 constexpr int kK2 = 64, kK2Steps = kK2 / 16, kA2Cols = kK2 / 2;
@@ -239,7 +239,7 @@ __device__ __forceinline__ void h2_to_tmem(uint32_t slot_lane) {
 #endif
 
 template <int L>
-__global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetParams p, int *timeout_flag, long long *trace) {
+__global__ void __maxnreg__(96) vnet_decode_tc_kernel(VnetParams p, int *timeout_flag, long long *trace) {
     static_assert(L <= 6, "tcgen05 variant: the priors of one stage must fit a 64-column TMEM region");
     using D = TrellisDims<L>;
     constexpr int S = D::S, C = D::C, NCH = D::NCH, NW = tc::kProdWarps + tc::kConsWarps;
@@ -338,27 +338,22 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
                     // Compute this stage's pieces into registers BEFORE waiting for the slot: the sigmoid/split work
                     // then overlaps the MMAs and the consumer of the stage that still owns the slot.
                     TC_TRACE(0, tid == 0);
-                    TC_TRACE(24 + warp, lane == 0);
-                    // k-steps per producer warp: warps 0-3 take steps 0..2 (24 pairs of hidden units), warps 4-7 take
-                    // steps 3..6 (26 pairs + the bias/padding columns), so both halves finish together
-                    constexpr int NKS = 4;
-                    const int c_base = warp < 4 ? 0 : 3;
+                    TC_TRACE(24 + warp, lane == 0 && warp < 8);
+                    // k-steps per producer warp (three warps per TMEM lane quadrant): steps 0-1 | 2-3 | 4-6, i.e. 16 | 16 | 18
+                    // pairs of hidden units (the last step holds pairs 48, 49 and the bias / padding columns)
+                    constexpr int NKS = 3;
+                    const int part = warp >> 2, c_base = 2 * part;
                     uint32_t vh[NKS][8], vl[NKS][8];
-                    if (warp < 4) {
 #pragma unroll
-                        for (int i = 0; i < 3; i++) tc::compute_chunk<false>(sP_addr, i, yy, vh[i], vl[i]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 3; i++) tc::compute_chunk<false>(sP_addr, 3 + i, yy, vh[i], vl[i]);
-                        tc::compute_chunk<true>(sP_addr, 6, yy, vh[3], vl[3]);
-                    }
+                    for (int i = 0; i < 2; i++) tc::compute_chunk<false>(sP_addr, c_base + i, yy, vh[i], vl[i]);
+                    if (part == 2) tc::compute_chunk<true>(sP_addr, 6, yy, vh[2], vl[2]);
                     TC_TRACE(1, tid == 0);
                     tc::mbar_wait(smem_addr(&slot_free[slot]), (use & 1) ^ 1, timeout_flag);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     TC_TRACE(2, tid == 0);
 #pragma unroll
                     for (int i = 0; i < NKS; i++) {
-                        if (warp >= 4 || i < 3) {
+                        if (part == 2 || i < 2) {
                             tc::tmem_st8(slot_lane + tc::oAh + (c_base + i) * 8, vh[i]);
                             tc::tmem_st8(slot_lane + tc::oAl + (c_base + i) * 8, vl[i]);
                         }
@@ -366,7 +361,7 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1) vnet_decode_tc_kernel(VnetP
                     asm volatile("tcgen05.wait::st.sync.aligned;");
                     asm volatile("tcgen05.fence::before_thread_sync;");
                     TC_TRACE(3, tid == 0);
-                    TC_TRACE(16 + warp, lane == 0);
+                    TC_TRACE(16 + warp, lane == 0 && warp < 8);
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(smem_addr(&a_full[slot]));  // one arrival per producer warp
                     __syncwarp();
