@@ -15,10 +15,10 @@ struct mvn_ctx {
     int T_max = 0;
     int L = 0;
     int S = 0;
-    static constexpr int kSlots = 3;   // H2D of chunk i+1, kernel of chunk i and D2H of chunk i-1 in flight together
-    cudaStream_t st[kSlots] = {nullptr, nullptr, nullptr};
-    float *d_y[kSlots] = {nullptr, nullptr, nullptr};
-    void *d_out[kSlots] = {nullptr, nullptr, nullptr};
+    static constexpr int kSlots = 4;   // H2D of chunk i+1, kernel of chunk i and D2H of chunk i-1 in flight together (+1 slack)
+    cudaStream_t st[kSlots] = {};
+    float *d_y[kSlots] = {};
+    void *d_out[kSlots] = {};
     float *d_w = nullptr;   // packed w1,b1,w2,b2,w3,b3
     float *d_sp = nullptr;  // state priors table (VA), up to sp_cap floats
     int64_t sp_cap = 0;

@@ -27,15 +27,17 @@ def main():
     from python_code.ecc.rs_main import encode
     out = {}
     with tempfile.TemporaryDirectory() as tmp:
-        for tag, snr, fading in (('a', 9.0, True), ('b', 6.0, False)):
+        for tag, snr, fading, meta in (('a', 9.0, True, False), ('b', 6.0, False, False), ('m', 9.0, True, True),
+                                       ('n', 7.0, True, True)):
             wd = os.path.join(tmp, f'w_online_{tag}')
             os.makedirs(wd, exist_ok=True)
             torch.manual_seed(21)
             tr = METAVNETTrainer(memory_length=4, use_ecc=True, n_symbols=2, val_frames=3, subframes_in_frame=4,
                                  train_frames=1, val_block_length=120, fading_in_channel=fading, fading_in_decoder=False,
                                  channel_coefficients='time_decay', self_supervised=True, self_supervised_iterations=4,
-                                 ser_thresh=0.02, online_meta=False, buffer_empty=True, lr=1e-3, weights_dir=wd,
-                                 eval_mode='by_word')
+                                 ser_thresh=0.02 if tag != 'n' else 0.05, online_meta=meta, buffer_empty=True, lr=1e-3,
+                                 weights_dir=wd, eval_mode='by_word', meta_subframes=4, meta_train_iterations=2,
+                                 meta_j_num=3, window_size=1, MAML=(tag != 'n'), meta_lr=0.1, weights_init='last_frame')
             tr.deep_learning_setup()
             # supervised warm-up on separately drawn words, so that the run starts from a detector that mostly works
             with torch.no_grad():
@@ -66,7 +68,23 @@ def main():
                 _o(tx, rx)
                 _after.append(np.concatenate([p.detach().numpy().reshape(-1) for p in _tr.detector.parameters()]))
             tr.online_training = recording_online
+            saved_after = []
+            if meta:          # weights right after every online meta-training round (what copy_model saves, trainer.py:343)
+                orig_loop = tr.meta_train_loop
+                jhats = []
+
+                def recording_loop(rx, tx, sidx, qidx, _o=orig_loop, _j=jhats, _s=saved_after, _tr=tr):
+                    r = _o(rx, tx, sidx, qidx)
+                    _j.append(int(qidx[0]))
+                    _s.append(np.concatenate([p.detach().numpy().reshape(-1) for p in _tr.detector.parameters()]))
+                    return r
+                tr.meta_train_loop = recording_loop
+            torch.manual_seed(1000 + len(tag) + ord(tag))
+            out[f'{tag}_seed'] = np.array([1000 + len(tag) + ord(tag)])
             ser = tr.eval_by_word(snr, 0.2)
+            if meta:
+                out[f'{tag}_jhat'] = np.array(jhats)
+                out[f'{tag}_theta_meta'] = np.stack(saved_after).astype(np.float32) if saved_after else np.zeros((0, 1), np.float32)
             cls.__getitem__ = orig_fn
             out[f'{tag}_bits'] = drawn['b'].astype(np.uint8)
             out[f'{tag}_y'] = drawn['y'].astype(np.float32)
@@ -74,6 +92,8 @@ def main():
             out[f'{tag}_theta_after'] = np.stack(after).astype(np.float32)
             out[f'{tag}_data_indices'] = tr.data_indices.numpy()
             out[f'{tag}_cfg'] = np.array([tr.memory_length, tr.n_symbols, tr.self_supervised_iterations, tr.ser_thresh, tr.lr])
+            out[f'{tag}_meta_cfg'] = np.array([int(meta), tr.meta_subframes, tr.meta_train_iterations, tr.meta_j_num,
+                                               tr.window_size, int(tr.MAML), tr.meta_lr])
             print(tag, 'ser by word', ser, 'trained after', len(after), 'blocks')
     mg.save('online', **out)
 
