@@ -35,6 +35,9 @@
 
 namespace mvn {
 
+#ifndef MVN_CONS_PARK
+#define MVN_CONS_PARK true
+#endif
 namespace tc {
 constexpr int kM = 128, kN = 64, kK = 112;    // MMA tile: frames x padded outputs x padded hidden units (+ bias column)
 constexpr int kKSteps = kK / 16;              // UMMA_K = 16 for fp16
@@ -95,15 +98,23 @@ __device__ __forceinline__ void tmem_ld2(uint32_t addr, float *r) {
 // try_wait with a suspend-time hint: the waiting warp is parked by the hardware until the phase completes (or the
 // hint expires) instead of spinning.  A spinning warp competes for the issue slots of its scheduler; the MMA warp
 // waits most of the time and made the producers that share its scheduler the slowest of the CTA (pipeline trace).
+template <bool PARK = true>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int *timeout_flag) {
     uint32_t done = 0;
     int spins = 0;
     while (!done) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(done)
-            : "r"(bar), "r"(parity), "r"(0x989680)
-            : "memory");
+        if (PARK)
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                : "=r"(done)
+                : "r"(bar), "r"(parity), "r"(0x989680)
+                : "memory");
+        else
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                : "=r"(done)
+                : "r"(bar), "r"(parity)
+                : "memory");
         if (!done && ++spins > (1 << 16)) {  // never expected; keeps a bug from hanging the GPU
             if (timeout_flag) *timeout_flag = 1;
             break;
@@ -415,7 +426,7 @@ __global__ void __maxnreg__(96) vnet_decode_tc_kernel(VnetParams p, int *timeout
                     const uint32_t slot = n & 1, use = n >> 1;
                     const uint32_t ts = tmem + slot * tc::kSlotCols, slot_lane = ts + lane_base;
                     TC_TRACE(6, warp == tc::kProdWarps && lane == 0);
-                    tc::mbar_wait(smem_addr(&d_full[slot]), use & 1, timeout_flag);
+                    tc::mbar_wait<MVN_CONS_PARK>(smem_addr(&d_full[slot]), use & 1, timeout_flag);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     TC_TRACE(7, warp == tc::kProdWarps && lane == 0);
                     tc::h2_to_tmem(slot_lane);                       // layer-2 result -> ReLU -> A operand of layer 3
@@ -438,7 +449,7 @@ __global__ void __maxnreg__(96) vnet_decode_tc_kernel(VnetParams p, int *timeout
                     TC_TRACE(10, warp == tc::kProdWarps && lane == 0);
                     __syncwarp();
                     bits |= tr.decide() << tt;                       // metrics entering this stage; overlaps the MMAs
-                    tc::mbar_wait(smem_addr(&d2_full), n & 1, timeout_flag);
+                    tc::mbar_wait<MVN_CONS_PARK>(smem_addr(&d2_full), n & 1, timeout_flag);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     TC_TRACE(11, warp == tc::kProdWarps && lane == 0);
                     float *dst = (p.priors_out && b < p.B) ? p.priors_out + (b * p.T + t0 + tt) * S : nullptr;
