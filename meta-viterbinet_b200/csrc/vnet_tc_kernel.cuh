@@ -171,17 +171,28 @@ __device__ __forceinline__ void split2_pre(u64 g, uint32_t &whi, uint32_t &wlo) 
     whi = *reinterpret_cast<const uint32_t *>(&hi);
     wlo = *reinterpret_cast<const uint32_t *>(&lo);
 }
-// X = 2048 h (consumer side) -> fp16x2 words of hi = fp16(h) and lo = fp16((h - hi) 2048): the A operand of layer 3
-__device__ __forceinline__ void split2_f16(u64 X, uint32_t &whi, uint32_t &wlo) {
+// X = 2048 a2 (consumer side, BEFORE the ReLU) -> fp16x2 words of the A operand of layer 3: hi = fp16(relu(a2)) rounded
+// toward zero, lo = fp16((relu(a2) - hi) 2048).  The ReLU rides on the two conversions (cvt.relu): with hi rounded
+// toward zero the remainder X - 2048 hi is >= 0 whenever X >= 0, and equals X < 0 otherwise, so clamping both
+// conversions at zero is exactly relu on the value and costs no instruction.
+__device__ __forceinline__ uint32_t cvt_f16x2_relu_rz(float hi_half, float lo_half) {
+    uint32_t d;
+    asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_half), "f"(lo_half));
+    return d;
+}
+__device__ __forceinline__ uint32_t cvt_f16x2_relu_rn(float hi_half, float lo_half) {
+    uint32_t d;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_half), "f"(lo_half));
+    return d;
+}
+__device__ __forceinline__ void split2_relu(u64 X, uint32_t &whi, uint32_t &wlo) {
     float h0, h1;
-    unpack2(mul2(X, 0x3a0000003a000000ull), h0, h1);   // h = X / 2048
-    const __half2 hi = __floats2half2_rn(h0, h1);
-    const float2 f = __half22float2(hi);
+    unpack2(mul2(X, 0x3a0000003a000000ull), h0, h1);   // a2 = X / 2048
+    whi = cvt_f16x2_relu_rz(h1, h0);                    // low half = even unit
+    const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&whi));
     float r0, r1;
-    unpack2(fma2(pack2(f.x, f.y), 0xc5000000c5000000ull, X), r0, r1);   // X - 2048 f, exact up to the final rounding
-    const __half2 lo = __floats2half2_rn(r0, r1);
-    whi = *reinterpret_cast<const uint32_t *>(&hi);
-    wlo = *reinterpret_cast<const uint32_t *>(&lo);
+    unpack2(fma2(pack2(f.x, f.y), 0xc5000000c5000000ull, X), r0, r1);   // X - 2048 hi, exact
+    wlo = cvt_f16x2_relu_rn(r1, r0);
 }
 // one k-step (16 hidden units = 8 TMEM columns) of this thread's frame: sigmoid -> split into registers
 template <bool LAST>
@@ -215,10 +226,9 @@ __device__ __forceinline__ void h2_to_tmem(uint32_t slot_lane) {
         for (int q = 0; q < 8; q++) {
             const int k = 16 * c0 + 2 * q;
             if (k + 1 < kH2) {
-                // D_main + D_corr / 2048 = 2048 (W2 h1 + b2): ReLU keeps the scale, split2_f16 takes the scaled value
-                const float x0 = fmaxf(fmaf(c[2 * q], kInvScale, m[2 * q]), 0.f);
-                const float x1 = fmaxf(fmaf(c[2 * q + 1], kInvScale, m[2 * q + 1]), 0.f);
-                split2_f16(pack2(x0, x1), vh[q], vl[q]);
+                // D_main + D_corr / 2048 = 2048 (W2 h1 + b2), both units of the pair in one packed FMA; ReLU and the
+                // hi / lo split in split2_relu
+                split2_relu(fma2(pack2(c[2 * q], c[2 * q + 1]), 0x3a0000003a000000ull, pack2(m[2 * q], m[2 * q + 1])), vh[q], vl[q]);
             } else {  // k2 = 50: bias column (1.0 in the low half); beyond: zero padding
                 vh[q] = (k == kH2) ? 0x00003c00u : 0u;
                 vl[q] = 0u;
