@@ -315,6 +315,30 @@ def test_error_rates_golden(mvn, k):
     assert np.array_equal(idx.cpu().numpy(), g[f'idx_{k}'])
 
 
+@pytest.mark.parametrize('L', [1, 4, 5, 6])
+def test_vnet_fused_edge_shapes_with_counters(mvn, fused_impl, L):
+    """no stage at all, one symbol, exact tile multiples, tile + 1, stages ending mid-tile; fused counters exact;
+    the tensor-core kernel's pipeline-timeout flag stays clear"""
+    import ctypes
+    rng = np.random.RandomState(900 + L)
+    S = 2 ** L
+    w = [(rng.randn(*s) * sc).astype(np.float32) for s, sc in
+         [((100, 1), .7), ((100,), .5), ((50, 100), .15), ((50,), .1), ((S, 50), .3), ((S,), .1)]]
+    wd = [cu(a) for a in w]
+    for B, T, n in ((3, 5, 0), (129, 64, 64), (1, 1, 1), (300, 97, 50), (128, 32, 32), (257, 120, 120)):
+        y = (rng.randn(B, T) * 1.5).astype(np.float32)
+        tgt = rng.randint(0, 2, size=(B, T)).astype(np.float32)
+        cnt = mvn.ops.new_counters()
+        dec, pri = mvn.ops.vnet_decode(cu(y), wd, n_stages=n, return_priors=True, target=cu(tgt), counters=cnt)
+        dec, pri = dec.cpu().numpy(), pri.cpu().numpy()
+        ref = orc.vnet_decode_from_priors(pri, n)[0] if n > 0 else np.zeros_like(dec)
+        assert np.array_equal(dec, ref), (L, B, T, n)
+        assert cnt.cpu().tolist() == [int((dec != tgt).sum()), int((dec != tgt).any(axis=1).sum()), B * T, B]
+    f = mvn._lib.load().mvn_debug_tc_timeout
+    f.restype = ctypes.c_int
+    assert f() == 0
+
+
 def test_error_counts_pilots_and_fused_counters(mvn, fused_impl):
     g = load_golden('vnet')
     w, y = _w(g, 'trained_w'), g['y']
