@@ -15,15 +15,17 @@
 // 2048 (W2 h1 + b2), which is what the ReLU / split of layer 3 wants as input.
 //
 // Warp-specialised pipeline over a two-slot TMEM ring; one frame = one TMEM lane, 128 frames per CTA tile:
-//   8 producer warps : y -> 100 sigmoids -> fp16 hi/lo split -> tcgen05.st  A_hi, A_lo [128 x 112] (2 x 56 columns)
-//                      (warps w and w+4 serve the same 32 frames and split the hidden units)
+//  12 producer warps : y -> 100 sigmoids -> fp16 hi/lo split -> tcgen05.st  A_hi, A_lo [128 x 112] (2 x 56 columns)
+//                      (three warps per TMEM lane quadrant serve the same 32 frames and split the hidden units)
 //   1 MMA warp       : per stage 7 + 7 tcgen05.mma.kind::f16 (M=128, K=16; N=128 for A_hi x [W2_hi | W2_lo], N=64 for
 //                      A_lo x W2_hi), A from TMEM, B from shared memory in the canonical K-major no-swizzle layout;
 //                      tcgen05.commit -> d_full[slot]
-//   4 consumer warps : tcgen05.ld D_main/D_corr -> combine -> ReLU -> the same hi/lo split -> tcgen05.st as the A
+//   4 converter warps: tcgen05.ld D_main/D_corr -> combine -> ReLU -> the same hi/lo split -> tcgen05.st as the A
 //                      operand of LAYER 3, which also runs on the tensor core (4 + 4 MMAs, W3 pieces and b3 in
-//                      shared memory, issued by one consumer thread); tcgen05.ld of the 16 priors -> ACS on the
-//                      frame's 8 private path metrics, decision bit, outputs, BER.  No weight traffic on the LSU.
+//                      shared memory, issued by one converter thread)
+//   4 consumer warps : tcgen05.ld of the 16 priors -> ACS on the frame's 8 private path metrics, decision bit,
+//                      outputs, BER.  Converters and consumers pipeline across the two slots: stage n+1 is converted
+//                      while layer 3 of stage n runs and its ACS is done.  No weight traffic on the LSU.
 // The sigmoid/split/MMA work of later stages does not depend on the ACS result of earlier ones (only the
 // decision chain is sequential), which is what lets producers and the tensor core run ahead.
 // TMEM: 2 x (64 + 64 + 56 + 56) columns of the 512-column allocation, one CTA per SM; layer 3 reuses the slot's
@@ -55,7 +57,8 @@ constexpr float kScale = 2048.f, kInvScale = 1.f / 2048.f;
 constexpr uint32_t kLBO = (2 * kN / 8) * 128; // bytes between consecutive 16-byte K chunks (k-chunk stride)
 constexpr uint32_t kSBO = 128;                // bytes between 8-row groups along N
 constexpr int kBBytes = (kK / 8) * (2 * kN / 8) * 128;
-constexpr int kProdWarps = 12, kConsWarps = 4, kThreadsTc = 32 * (kProdWarps + kConsWarps + 1);  // + one MMA-issue warp
+constexpr int kProdWarps = 12, kConvWarps = 4, kConsWarps = 4;   // producers | h2 converters | ACS consumers
+constexpr int kThreadsTc = 32 * (kProdWarps + kConvWarps + kConsWarps + 1);  // + one MMA-issue warp
 // layer 3 on the tensor core as well: D2[128 x 16] = h2[128 x 64] W3^T, K2 = 50 hidden units + bias column, padded
 // (N2 = max(16, n_states) output columns, so up to 64 states fit the slot's 64-column D regions)
 constexpr int kK2 = 64, kK2Steps = kK2 / 16, kA2Cols = kK2 / 2;
@@ -245,7 +248,7 @@ __device__ __forceinline__ void h2_to_tmem(uint32_t slot_lane) {
 }  // namespace tc
 
 // Optional pipeline trace (debug builds only, -DMVN_TC_TRACE): CTA 0 records clock64() at the key points of the
-// first 64 stages, 32 event slots per stage, into trace[stage*32 + event]; slots 16+w / 24+w: start / stored of producer warp w.
+// first 64 stages, 32 event slots per stage, into trace[stage*32 + event]; slots 16+w: A stored by producer warp w (12 warps), 28+w: start of producer warps 0..3.
 #ifdef MVN_TC_TRACE
 #define TC_TRACE(ev, cond)                                                                               \
     do {                                                                                                 \
@@ -263,15 +266,15 @@ __device__ __forceinline__ void h2_to_tmem(uint32_t slot_lane) {
 #endif
 
 template <int L>
-__global__ void __maxnreg__(96) vnet_decode_tc_kernel(VnetParams p, int *timeout_flag, long long *trace) {
+__global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, int *timeout_flag, long long *trace) {
     static_assert(L <= 6, "tcgen05 variant: the priors of one stage must fit a 64-column TMEM region");
     using D = TrellisDims<L>;
-    constexpr int S = D::S, C = D::C, NCH = D::NCH, NW = tc::kProdWarps + tc::kConsWarps;
+    constexpr int S = D::S, C = D::C, NCH = D::NCH, NW = tc::kProdWarps + tc::kConvWarps + tc::kConsWarps;
     constexpr int N2 = tc::n2_of(S), kB2Bytes = tc::b2_bytes(S);
     constexpr uint32_t kLBO2 = (2 * N2 / 8) * 128;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint32_t tmem_base_s;
-    __shared__ __align__(8) uint64_t d_full[2], slot_free[2], a_full[2], d2_full;
+    __shared__ __align__(8) uint64_t d_full[2], slot_free[2], a_full[2], d2_full[2];
     constexpr int NT_TILES = tc::kProdWarps + tc::kConsWarps;                    // producers and consumers stage tiles
     uint8_t *sB = smem_raw;                                                      // W2 pieces, hi rows | lo rows
     float *tiles = reinterpret_cast<float *>(smem_raw + tc::kBBytes);            // one 32x32 tile per such warp
@@ -279,8 +282,10 @@ __global__ void __maxnreg__(96) vnet_decode_tc_kernel(VnetParams p, int *timeout
     uint8_t *sB2 = reinterpret_cast<uint8_t *>(sP + 4 * (tc::kK / 2));           // W3 (+ b3 column) pieces: hi | lo
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, quad = warp & 3;
     const bool producer = warp < tc::kProdWarps;
+    const bool converter = !producer && warp < tc::kProdWarps + tc::kConvWarps;
     const bool mma_warp = warp == NW;
-    float *tile = tiles + (warp < NT_TILES ? warp : 0) * kTileFloats;
+    // tiles: one per producer warp (y) and one per consumer warp (targets); converters and the MMA warp use none
+    float *tile = tiles + (producer ? warp : tc::kProdWarps + quad) * kTileFloats;
 
     // ---- W2 (and b2 as column k=100) -> fp16 hi / scaled-lo pieces in the canonical K-major layout
     for (int idx = tid; idx < tc::kN * tc::kK; idx += tc::kThreadsTc) {
@@ -316,10 +321,10 @@ __global__ void __maxnreg__(96) vnet_decode_tc_kernel(VnetParams p, int *timeout
 #pragma unroll
         for (int s = 0; s < 2; s++) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&d_full[s])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&d2_full[s])));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&slot_free[s])), "n"(tc::kConsWarps));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&a_full[s])), "n"(tc::kProdWarps));
         }
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&d2_full)));
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     if (warp == 0) {
@@ -347,6 +352,7 @@ __global__ void __maxnreg__(96) vnet_decode_tc_kernel(VnetParams p, int *timeout
     uint32_t n = 0;                                        // running stage counter: slot = n & 1, use = n >> 1
 
     if (producer) {
+        int rot = 0;  // which of the quadrant's three warps takes the seventh k-step in this stage
         for (int64_t ct = blockIdx.x; ct < n_cta_tiles; ct += gridDim.x) {
             const int64_t row0 = (ct * 4 + quad) * 32;
             for (int t0 = 0; t0 < p.T; t0 += 32) {
@@ -362,30 +368,36 @@ __global__ void __maxnreg__(96) vnet_decode_tc_kernel(VnetParams p, int *timeout
                     // Compute this stage's pieces into registers BEFORE waiting for the slot: the sigmoid/split work
                     // then overlaps the MMAs and the consumer of the stage that still owns the slot.
                     TC_TRACE(0, tid == 0);
-                    TC_TRACE(24 + warp, lane == 0 && warp < 8);
-                    // k-steps per producer warp (three warps per TMEM lane quadrant): steps 0-1 | 2-3 | 4-6, i.e. 16 | 16 | 18
-                    // pairs of hidden units (the last step holds pairs 48, 49 and the bias / padding columns)
+                    TC_TRACE(28 + warp, lane == 0 && warp < 4);
+                    // k-steps per producer warp (three warps per TMEM lane quadrant): steps 0-1 | 2-3 | 4-5, 16 pairs of hidden
+                    // units each; the seventh step (pairs 48, 49 and the bias / padding columns) rotates among the three
+                    // warps from stage to stage, so that over three stages every warp computes 50 pairs (a fixed owner
+                    // made that warp the pace-setter of the whole CTA: pipeline trace)
                     constexpr int NKS = 3;
                     const int part = warp >> 2, c_base = 2 * part;
+                    const bool last_step = rot == part;
                     uint32_t vh[NKS][8], vl[NKS][8];
 #pragma unroll
                     for (int i = 0; i < 2; i++) tc::compute_chunk<false>(sP_addr, c_base + i, yy, vh[i], vl[i]);
-                    if (part == 2) tc::compute_chunk<true>(sP_addr, 6, yy, vh[2], vl[2]);
+                    if (last_step) tc::compute_chunk<true>(sP_addr, 6, yy, vh[2], vl[2]);
                     TC_TRACE(1, tid == 0);
                     tc::mbar_wait<MVN_PROD_PARK>(smem_addr(&slot_free[slot]), (use & 1) ^ 1, timeout_flag);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     TC_TRACE(2, tid == 0);
 #pragma unroll
-                    for (int i = 0; i < NKS; i++) {
-                        if (part == 2 || i < 2) {
-                            tc::tmem_st8(slot_lane + tc::oAh + (c_base + i) * 8, vh[i]);
-                            tc::tmem_st8(slot_lane + tc::oAl + (c_base + i) * 8, vl[i]);
-                        }
+                    for (int i = 0; i < 2; i++) {
+                        tc::tmem_st8(slot_lane + tc::oAh + (c_base + i) * 8, vh[i]);
+                        tc::tmem_st8(slot_lane + tc::oAl + (c_base + i) * 8, vl[i]);
                     }
+                    if (last_step) {
+                        tc::tmem_st8(slot_lane + tc::oAh + 6 * 8, vh[2]);
+                        tc::tmem_st8(slot_lane + tc::oAl + 6 * 8, vl[2]);
+                    }
+                    rot = rot == 2 ? 0 : rot + 1;
                     asm volatile("tcgen05.wait::st.sync.aligned;");
                     asm volatile("tcgen05.fence::before_thread_sync;");
                     TC_TRACE(3, tid == 0);
-                    TC_TRACE(16 + warp, lane == 0 && warp < 8);
+                    TC_TRACE(16 + warp, lane == 0);
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(smem_addr(&a_full[slot]));  // one arrival per producer warp
                     __syncwarp();
@@ -421,11 +433,50 @@ __global__ void __maxnreg__(96) vnet_decode_tc_kernel(VnetParams p, int *timeout
                 }
             }
         }
+    } else if (converter) {
+        // h2 converters: layer-2 result of stage n -> ReLU -> hi/lo split -> A operand of layer 3 in the slot's A columns, then
+        // the layer-3 MMAs.  They work on stage n+1 (other slot) while layer 3 of stage n runs and the consumers finish it.
+        for (int64_t ct = blockIdx.x; ct < n_cta_tiles; ct += gridDim.x) {
+            for (int t0 = 0; t0 < p.T; t0 += 32) {
+                const int t_end = min(32, p.n_stages - t0);
+#pragma unroll 1
+                for (int tt = 0; tt < t_end; tt++, n++) {
+                    const uint32_t slot = n & 1, use = n >> 1;
+                    const uint32_t ts = tmem + slot * tc::kSlotCols, slot_lane = ts + lane_base;
+                    TC_TRACE(6, warp == tc::kProdWarps && lane == 0);
+                    tc::mbar_wait<MVN_CONS_PARK>(smem_addr(&d_full[slot]), use & 1, timeout_flag);
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+                    TC_TRACE(7, warp == tc::kProdWarps && lane == 0);
+                    tc::h2_to_tmem(slot_lane);
+                    asm volatile("tcgen05.fence::before_thread_sync;");
+                    TC_TRACE(8, warp == tc::kProdWarps && lane == 0);
+                    asm volatile("bar.sync 2, %0;" ::"n"(32 * tc::kConvWarps));
+                    TC_TRACE(9, warp == tc::kProdWarps && lane == 0);
+                    if (warp == tc::kProdWarps + 1 && tc::elect_one()) {  // one thread (not on the MMA warp's scheduler) issues layer 3: 4 + 4 MMAs
+                        asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll
+                        for (int j = 0; j < tc::kK2Steps; j++)   // priors_main | priors_corr = h2_hi [W3_hi | W3_lo]
+                            tc::mma_f16_ts(ts + tc::oDm, ts + tc::oAh + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2, kLBO2),
+                                           idesc2w, j > 0);
+#pragma unroll
+                        for (int j = 0; j < tc::kK2Steps; j++)   // priors_corr += h2_lo W3_hi
+                            tc::mma_f16_ts(ts + tc::oDm + N2, ts + tc::oAl + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2, kLBO2),
+                                           idesc2, 1);
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                            smem_addr(&d2_full[slot])));
+                    }
+                    TC_TRACE(10, warp == tc::kProdWarps && lane == 0);
+                    __syncwarp();
+                }
+            }
+        }
     } else {
+        // consumers: priors of stage n -> ACS on the frame's private path metrics -> decision bit, outputs, BER
         typename std::conditional<(L <= 5), RegTrellis<L>, SmemTrellis<L>>::type tr;
         if constexpr (L > 5)   // path metrics of the 128 frames of the tile: [2][H][128] floats behind the W3 pieces
-            tr.init(reinterpret_cast<float *>(sB2 + kB2Bytes), 32 * tc::kConsWarps, (warp - tc::kProdWarps) * 32 + lane);
+            tr.init(reinterpret_cast<float *>(sB2 + kB2Bytes), 32 * tc::kConsWarps, quad * 32 + lane);
         ErrAcc acc;
+        constexpr int kConsFirst = tc::kProdWarps + tc::kConvWarps;
         for (int64_t ct = blockIdx.x; ct < n_cta_tiles; ct += gridDim.x) {
             const int64_t row0 = (ct * 4 + quad) * 32;
             const int64_t b = row0 + lane;
@@ -438,33 +489,10 @@ __global__ void __maxnreg__(96) vnet_decode_tc_kernel(VnetParams p, int *timeout
                 for (int tt = 0; tt < t_end; tt++, n++) {
                     const uint32_t slot = n & 1, use = n >> 1;
                     const uint32_t ts = tmem + slot * tc::kSlotCols, slot_lane = ts + lane_base;
-                    TC_TRACE(6, warp == tc::kProdWarps && lane == 0);
-                    tc::mbar_wait<MVN_CONS_PARK>(smem_addr(&d_full[slot]), use & 1, timeout_flag);
+                    bits |= tr.decide() << tt;                       // metrics entering this stage; overlaps the wait
+                    tc::mbar_wait<MVN_CONS_PARK>(smem_addr(&d2_full[slot]), use & 1, timeout_flag);
                     asm volatile("tcgen05.fence::after_thread_sync;");
-                    TC_TRACE(7, warp == tc::kProdWarps && lane == 0);
-                    tc::h2_to_tmem(slot_lane);                       // layer-2 result -> ReLU -> A operand of layer 3
-                    asm volatile("tcgen05.fence::before_thread_sync;");
-                    TC_TRACE(8, warp == tc::kProdWarps && lane == 0);
-                    asm volatile("bar.sync 2, %0;" ::"n"(32 * tc::kConsWarps));
-                    TC_TRACE(9, warp == tc::kProdWarps && lane == 0);
-                    if (warp == tc::kProdWarps + 1 && tc::elect_one()) {  // one consumer thread (not on the MMA warp's scheduler) issues layer 3: 4 + 4 MMAs
-                        asm volatile("tcgen05.fence::after_thread_sync;");
-#pragma unroll
-                        for (int j = 0; j < tc::kK2Steps; j++)   // priors_main | priors_corr = h2_hi [W3_hi | W3_lo]
-                            tc::mma_f16_ts(ts + tc::oDm, ts + tc::oAh + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2, kLBO2),
-                                           idesc2w, j > 0);
-#pragma unroll
-                        for (int j = 0; j < tc::kK2Steps; j++)   // priors_corr += h2_lo W3_hi
-                            tc::mma_f16_ts(ts + tc::oDm + N2, ts + tc::oAl + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2, kLBO2),
-                                           idesc2, 1);
-                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(&d2_full)));
-                    }
-                    TC_TRACE(10, warp == tc::kProdWarps && lane == 0);
-                    __syncwarp();
-                    bits |= tr.decide() << tt;                       // metrics entering this stage; overlaps the MMAs
-                    tc::mbar_wait<MVN_CONS_PARK>(smem_addr(&d2_full), n & 1, timeout_flag);
-                    asm volatile("tcgen05.fence::after_thread_sync;");
-                    TC_TRACE(11, warp == tc::kProdWarps && lane == 0);
+                    TC_TRACE(11, warp == kConsFirst && lane == 0);
                     float *dst = (p.priors_out && b < p.B) ? p.priors_out + (b * p.T + t0 + tt) * S : nullptr;
                     // 16 source states per chunk: priors = D_main + D_corr / 2048, cost = -prior (vnet_detector.py:57)
                     auto chunk = [&](auto cc, bool last) {
@@ -475,7 +503,7 @@ __global__ void __maxnreg__(96) vnet_decode_tc_kernel(VnetParams p, int *timeout
                         asm volatile("tcgen05.wait::ld.sync.aligned;");
                         if (last) {
                             asm volatile("tcgen05.fence::before_thread_sync;");
-                            TC_TRACE(12, warp == tc::kProdWarps && lane == 0);
+                            TC_TRACE(12, warp == kConsFirst && lane == 0);
                             __syncwarp();
                             if (lane == 0) tc::mbar_arrive(smem_addr(&slot_free[slot]));  // the slot's A and D columns may be refilled
                         }
@@ -499,7 +527,7 @@ __global__ void __maxnreg__(96) vnet_decode_tc_kernel(VnetParams p, int *timeout
                         chunk(std::integral_constant<int, 3>{}, true);
                     }
                     tr.commit();
-                    TC_TRACE(13, warp == tc::kProdWarps && lane == 0);
+                    TC_TRACE(13, warp == kConsFirst && lane == 0);
                 }
                 __syncwarp();
                 if (p.decoded) {

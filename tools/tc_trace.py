@@ -40,6 +40,6 @@ for a, b, label in [(0, 1, 'producer compute'), (1, 2, 'producer waits for slot'
 print(f'  stage period (consumer)                  {float(np.median(np.diff(t[16:56, 13]))):8.0f}')
 mhz = (t[60, 0] - t[4, 0]) / max(1, (t[60, 14] - t[4, 14])) * 1000.0
 print(f'  effective SM clock during the kernel (clock64 / globaltimer over stages 4..60): {mhz:8.0f} MHz')
-print('  per producer warp, median over stages 16..55 (cycles): start -> stored | stored relative to warp 0')
-for w in range(8):
-    print(f'    warp {w}: {float(np.median(t[16:56, 16 + w] - t[16:56, 24 + w])):8.0f} | {float(np.median(t[16:56, 16 + w] - t[16:56, 16])):8.0f}')
+print('  A operand stored, per producer warp relative to warp 0 (median over stages 16..55, cycles); warps w, w+4, w+8 share a quadrant:')
+print('    ' + ' '.join(f'{float(np.median(t[16:56, 16 + w] - t[16:56, 16])):6.0f}' for w in range(12)))
+print('  start -> stored, producer warps 0..3: ' + ' '.join(f'{float(np.median(t[16:56, 16 + w] - t[16:56, 28 + w])):6.0f}' for w in range(4)))
