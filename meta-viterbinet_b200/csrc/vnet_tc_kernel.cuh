@@ -1,6 +1,6 @@
-// tcgen05 variant of the fused ViterbiNet kernel (memory_length <= 6): layer 2 of the priors MLP
-// ([symbols,100] x [100,50], 85 % of the flops) runs on the 5th-generation tensor cores, everything
-// else (sigmoid, ReLU, layer 3, ACS, decision) stays on the CUDA cores of the same CTA.
+// tcgen05 variant of the fused ViterbiNet kernel (memory_length <= 6): layers 2 and 3 of the priors MLP
+// ([symbols,100] x [100,50] and [symbols,50] x [50,S], 99 % of the flops) run on the 5th-generation tensor cores;
+// the sigmoid, the ReLU / operand splits, the ACS recursion and the decision stay on the CUDA cores of the same CTA.
 //
 // fp32 parity on fp16 tensor cores.  Each operand is split into two fp16 pieces with a scaled remainder,
 //     x = hi + lo / 2048,   hi = fp16(x),   lo = fp16((x - hi) * 2048)      (x - hi is exact in fp32),
@@ -61,7 +61,7 @@ constexpr int kProdWarps = 12, kConvWarps = 4, kConsWarps = 4;   // producers | 
 constexpr int kThreadsTc = 32 * (kProdWarps + kConvWarps + kConsWarps + 1);  // + one MMA-issue warp
 // layer 3 on the tensor core as well: D2[128 x 16] = h2[128 x 64] W3^T, K2 = 50 hidden units + bias column, padded
 // (N2 = max(16, n_states) output columns, so up to 64 states fit the slot's 64-column D regions)
-constexpr int kK2 = 64, kK2Steps = kK2 / 16, kA2Cols = kK2 / 2;
+constexpr int kK2 = 64, kK2Steps = kK2 / 16;
 __host__ __device__ constexpr int n2_of(int S) { return S < 16 ? 16 : S; }
 __host__ __device__ constexpr int b2_bytes(int S) { return (kK2 / 8) * (2 * n2_of(S) / 8) * 128; }  // hi | lo stacked along N
 
@@ -95,12 +95,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t addr, float *r) {
 #pragma unroll
     for (int i = 0; i < 16; i++) r[i] = __uint_as_float(u[i]);
 }
-__device__ __forceinline__ void tmem_ld2(uint32_t addr, float *r) {
-    uint32_t u0, u1;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(u0), "=r"(u1) : "r"(addr));
-    r[0] = __uint_as_float(u0);
-    r[1] = __uint_as_float(u1);
-}
 // try_wait with a suspend-time hint: the waiting warp is parked by the hardware until the phase completes (or the
 // hint expires) instead of spinning.  A spinning warp competes for the issue slots of its scheduler; the MMA warp
 // waits most of the time and made the producers that share its scheduler the slowest of the CTA (pipeline trace).
@@ -121,7 +115,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int *ti
                 : "=r"(done)
                 : "r"(bar), "r"(parity)
                 : "memory");
-        if (!done && ++spins > (1 << 16)) {  // never expected; keeps a bug from hanging the GPU
+        if (!done && ++spins > (PARK ? (1 << 16) : (1 << 26))) {  // never expected; keeps a bug from hanging the GPU
             if (timeout_flag) *timeout_flag = 1;
             break;
         }
@@ -143,7 +137,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // staged pair table: sP[k/2] = (w1'[k], w1'[k+1], b1'[k], b1'[k+1]) with w1' = -log2(e) w1, b1' = -log2(e) b1 - 11
 // (one LDS.128), so that 2^(w1' y + b1') = e^-a / 2048 and the reciprocal of  d' = e^-a / 2048 + 2^-11  is
 // g = 2048 sigmoid(a): the hidden activations are produced PRE-SCALED by 2^11.  Then the fp16 remainder g - fp16(g)
-// (< 1) needs no scaling of its own, it accumulates into D_main next to the hi piece, and the consumer's
+// (< 1) needs no scaling of its own, it accumulates into D_main next to the hi piece, and the converter's
 // x = D_main + D_corr / 2048 is 2048 (W2 h1 + b2), exactly the scaled value its own split wants.
 // The producers are bound by issue slots and by the XU (MUFU) pipe (16 lanes per clock per SM; pipeline trace in
 // profiles/): EX2 + RCP per unit is 200 MUFU per symbol.  Four reciprocals share ONE MUFU.RCP (Montgomery's trick:
@@ -177,7 +171,7 @@ __device__ __forceinline__ void split2_pre(u64 g, uint32_t &whi, uint32_t &wlo) 
     whi = *reinterpret_cast<const uint32_t *>(&hi);
     wlo = *reinterpret_cast<const uint32_t *>(&lo);
 }
-// X = 2048 a2 (consumer side, BEFORE the ReLU) -> fp16x2 words of the A operand of layer 3: hi = fp16(relu(a2)) rounded
+// X = 2048 a2 (converter warps, BEFORE the ReLU) -> fp16x2 words of the A operand of layer 3: hi = fp16(relu(a2)) rounded
 // toward zero, lo = fp16((relu(a2) - hi) 2048).  The ReLU rides on the two conversions (cvt.relu): with hi rounded
 // toward zero the remainder X - 2048 hi is >= 0 whenever X >= 0, and equals X < 0 otherwise, so clamping both
 // conversions at zero is exactly relu on the value and costs no instruction.
@@ -217,7 +211,7 @@ __device__ __forceinline__ void compute_chunk(uint32_t sP_addr, int c0, u64 yy, 
         }
     }
 }
-// consumer, step 1: h2 = relu(D_main + D_corr / 2048) of this thread's frame, split into fp16 hi / scaled lo,
+// converter warps: h2 = relu(D_main + D_corr / 2048) of this thread's frame, split into fp16 hi / scaled lo,
 // stored as the A operand of layer 3 (columns 0..31 of the slot's A_hi / A_lo regions, free after the MMAs of
 // layer 2); column k2 = 50 is the constant 1 that multiplies the b3 row of B2.
 __device__ __forceinline__ void h2_to_tmem(uint32_t slot_lane) {
