@@ -107,7 +107,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int *ti
             asm volatile(
                 "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                 : "=r"(done)
-                : "r"(bar), "r"(parity), "r"(0x989680)
+                : "r"(bar), "r"(parity), "r"(100000)   // suspend-time hint in ns: an upper bound of one nap, not a latency
                 : "memory");
         else
             asm volatile(
@@ -115,9 +115,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int *ti
                 : "=r"(done)
                 : "r"(bar), "r"(parity)
                 : "memory");
-        if (!done && ++spins > (PARK ? (1 << 16) : (1 << 26))) {  // never expected; keeps a bug from hanging the GPU
-            if (timeout_flag) *timeout_flag = 1;
-            break;
+        // never expected; keeps a bug from hanging the GPU: the first wait that gives up raises the flag, and every other
+        // wait of the grid bails out as soon as it sees it (the launch then ends quickly, with the flag set for the host)
+        if (!done && timeout_flag && (++spins & (PARK ? 7 : 1023)) == 0) {
+            if (*reinterpret_cast<volatile int *>(timeout_flag)) break;
+            if (spins > (PARK ? (1 << 12) : (1 << 24))) {
+                *timeout_flag = 1;
+                break;
+            }
         }
     }
 }
