@@ -297,7 +297,24 @@ static int launch_variant(VnetParams p, cudaStream_t st) {
     return MVN_OK;
 }
 
-__device__ int g_tc_timeout = 0;
+// Pipeline-timeout flag of the tcgen05 kernel, in mapped pinned host memory: the kernel raises it if one of its
+// mbarrier waits gives up (never expected: it would mean a protocol bug), the host sees it without a synchronisation and
+// refuses further launches loudly instead of returning words decoded from a broken pipeline.
+static int *g_tc_timeout_host = nullptr, *g_tc_timeout_dev = nullptr;
+static std::once_flag g_tc_timeout_once;
+static int *tc_timeout_flag() {
+    std::call_once(g_tc_timeout_once, [] {
+        if (cudaHostAlloc(reinterpret_cast<void **>(&g_tc_timeout_host), sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) !=
+            cudaSuccess) {
+            g_tc_timeout_host = nullptr;
+            return;
+        }
+        *g_tc_timeout_host = 0;
+        if (cudaHostGetDevicePointer(reinterpret_cast<void **>(&g_tc_timeout_dev), g_tc_timeout_host, 0) != cudaSuccess)
+            g_tc_timeout_dev = nullptr;
+    });
+    return g_tc_timeout_dev;
+}
 #ifdef MVN_TC_TRACE
 __device__ long long g_tc_trace[64 * 32];
 #endif
@@ -311,13 +328,20 @@ static int launch_tc(VnetParams p, cudaStream_t st) {
     p.n_warp_tiles = (p.B + 31) / 32;
     const int64_t need = (p.n_warp_tiles + 3) / 4;
     const int grid = int(std::min<int64_t>(need, sm_count()));
-    void *flag = nullptr;
-    MVN_CUDA(cudaGetSymbolAddress(&flag, g_tc_timeout));
+    int *flag = tc_timeout_flag();
+    if (!flag) {
+        set_error("vnet_decode (tcgen05): cannot allocate the mapped pipeline-timeout flag");
+        return MVN_ERR_CUDA;
+    }
+    if (*g_tc_timeout_host) {
+        set_error("vnet_decode (tcgen05): a pipeline wait timed out in an earlier launch; results since then are invalid");
+        return MVN_ERR_CUDA;
+    }
     void *trace = nullptr;
 #ifdef MVN_TC_TRACE
     MVN_CUDA(cudaGetSymbolAddress(&trace, g_tc_trace));
 #endif
-    kern<<<grid, tc::kThreadsTc, smem, st>>>(p, static_cast<int *>(flag), static_cast<long long *>(trace));
+    kern<<<grid, tc::kThreadsTc, smem, st>>>(p, flag, static_cast<long long *>(trace));
     note_launch();
     MVN_CUDA(cudaGetLastError());
     return MVN_OK;
@@ -451,11 +475,7 @@ extern "C" int mvn_debug_set_variant(int v) {
     return old;
 }
 
-extern "C" int mvn_debug_tc_timeout(void) {
-    int v = -1;
-    cudaMemcpyFromSymbol(&v, mvn::g_tc_timeout, sizeof(int));
-    return v;
-}
+extern "C" int mvn_debug_tc_timeout(void) { return mvn::g_tc_timeout_host ? *mvn::g_tc_timeout_host : 0; }
 
 #ifdef MVN_TC_TRACE
 extern "C" int mvn_debug_tc_trace(long long *host_out) {
