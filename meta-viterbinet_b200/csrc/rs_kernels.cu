@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(32 * kRsWarps) rs_encode_kernel(const float *_
 static bool rows_vec_ok(const void *p, int ld) { return (reinterpret_cast<uintptr_t>(p) % 16 == 0) && (ld % 4 == 0); }
 
 static int rs_grid(int64_t B) {
-    return int(std::max<int64_t>(1, std::min<int64_t>((B + kRsWarps - 1) / kRsWarps, int64_t(sm_count()) * 8)));
+    return int(std::max<int64_t>(1, std::min<int64_t>((B + kRsWarps - 1) / kRsWarps, int64_t(sm_count()) * 16)));
 }
 
 }  // namespace mvn

@@ -88,8 +88,16 @@ def _meta_round(trainer, buffers, saved, cfg, on_meta_step):
         source = saved
     elif torch.is_tensor(init):                              # 'meta_training': the stored meta-trained weights
         source = ops.dev_f32(init).reshape(R, -1)
+    elif callable(init):                                     # 'random': fresh weights AND a fresh optimizer (trainer.py:357-359)
+        source = trainer.theta.clone()
+        source[eligible] = ops.dev_f32(init(eligible)).reshape(len(eligible), -1)
+        z = el.unsqueeze(1)
+        trainer.adam_m.copy_(torch.where(z, torch.zeros_like(trainer.adam_m), trainer.adam_m))
+        trainer.adam_v.copy_(torch.where(z, torch.zeros_like(trainer.adam_v), trainer.adam_v))
+        trainer.adam_step.copy_(torch.where(el, torch.zeros_like(trainer.adam_step), trainer.adam_step))
     else:
-        raise ValueError("weights_init must be 'last_frame' or a [R,P] tensor of meta-trained weights")
+        raise ValueError("weights_init must be 'last_frame', a [R,P] tensor of meta-trained weights, or a callable "
+                         "runs -> [len(runs), P] fresh weights ('random')")
     trainer.theta.copy_(torch.where(el.unsqueeze(1), source, trainer.theta))
     window = cfg['window_size']
     for _ in range(cfg['meta_train_iterations']):
@@ -131,7 +139,8 @@ def eval_by_word(trainer, info_bits, received, n_symbols, ser_thresh, data_mask=
     online_meta: every ``meta_subframes`` words (trainer.py:331) run ``meta_train_iterations`` rounds of (FO-)MAML steps on
     the replay buffer with ``meta_j_num`` random query indices each (``draw(run, high, count)`` -> list of indices;
     default: the reference's torch.unique(torch.randint(...))), support = ``window_size`` preceding words, starting
-    from ``weights_init`` ('last_frame' = the saved weights, or a [R,P] tensor = the stored meta-trained weights);
+    from ``weights_init`` ('last_frame' = the saved weights, a [R,P] tensor = the stored meta-trained weights, or a callable
+    runs -> fresh weights = the reference's 'random', which also restarts the optimizer);
     ``trainer.meta_lr`` is the inner step.  init_buffer = (label words [R,n0,T], received [R,n0,T]) starts with a
     filled, sliding buffer (``buffer_empty: False``).
     Returns ser_by_word [R, N] float64 (0 for pilots), as trainer.py:354 returns per run."""

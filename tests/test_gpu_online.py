@@ -169,3 +169,12 @@ def test_online_meta_with_initial_sliding_buffer_and_wider_window(mvn):
     with pytest.raises(ValueError):
         mvn.online.eval_by_word(tr, info, rx, int(nsym), float(thresh), online_meta=True, meta_subframes=4,
                                 weights_init='random', init_buffer=(init_tx, rx[:, :5]))
+    # 'random' re-initialisation is a callable: fresh weights and a fresh optimizer for the runs that meta-train
+    fresh = theta0 * 0.5
+    calls = []
+    tr2 = mvn.BatchedVNetTrainer(theta0, int(L), lr=float(lr), meta_lr=0.1)
+    mvn.online.eval_by_word(tr2, info[:, :5], rx[:, :5], int(nsym), float(thresh), subframes_in_frame=4, iterations=1,
+                            self_supervised=False, online_meta=True, meta_subframes=4, meta_train_iterations=1, meta_j_num=1,
+                            second_order=False, init_buffer=(init_tx, rx[:, :5]), draw=lambda run, high, count: [1],
+                            weights_init=lambda runs: (calls.append(list(runs)) or fresh[runs]))
+    assert calls == [[0, 1]] and tr2.adam_step.tolist() == [1, 1]      # one round at word 4: restart, then one step
