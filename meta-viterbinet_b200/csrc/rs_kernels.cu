@@ -124,13 +124,23 @@ __global__ void __launch_bounds__(32 * kRsWarps) rs_decode_kernel(const float *_
             lg[q] = byte ? int(s_log[byte]) : -1;
             ex[q] = (n - 1 - j) % 255;
         }
-        // ---- syndromes S_i = r(2^i) (rs_decoder.py:37-48)
+        // ---- syndromes S_i = r(2^i) (rs_decoder.py:37-48).  The exponent of byte j in S_i is log(byte) + i (n-1-j) mod 255:
+        // kept as a running index per byte (one add and one conditional subtract per syndrome instead of a multiply
+        // and a modulo); S_0 is the plain XOR of the bytes.
         int any = 0;
+        int idx[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) idx[q] = lg[q];
         for (int i = 0; i < nsym; i++) {
             int part = 0;
 #pragma unroll
-            for (int q = 0; q < 8; q++)
-                if (lg[q] >= 0) part ^= s_exp[(lg[q] + i * ex[q]) % 255];
+            for (int q = 0; q < 8; q++) {
+                if (lg[q] >= 0) {
+                    part ^= s_exp[idx[q]];
+                    const int nx = idx[q] + ex[q];
+                    idx[q] = nx >= 255 ? nx - 255 : nx;
+                }
+            }
             part = warp_xor(part);
             if (lane == 0) s.synd[i] = uint8_t(part);
             any |= part;
