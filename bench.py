@@ -378,8 +378,8 @@ def main():
             'roofline': roofline, 'cpu_baseline': cpu_baseline,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': frames * T * 4 * world,
                     'd2h_bytes_per_step': frames * T * 4 * world, 'matches_device_path': e2e_ok,
-                    'api': 'mvn_ctx_vnet_decode_host (pinned host buffers, chunks of two kernel waves, 4 streams); '
-                           'PCIe-bound: ~41 GB/s in each direction at once',
+                    'api': 'mvn_ctx_vnet_decode_host (pinned host buffers, chunks of two kernel waves, 6 streams); PCIe-bound: '
+                           'the box moves 49.9 GB/s in each direction at once (tools/pcie_ceiling.py) = 12.5 G symbols/s',
                     'bit_packed_output': {'value': e2e_bits_value, 'unit': UNIT,
                                           'd2h_bytes_per_step': frames * ((T + 31) // 32) * 4 * world}},
             'gpu_launches': launches, 'clocks': clocks,

@@ -15,7 +15,7 @@ struct mvn_ctx {
     int T_max = 0;
     int L = 0;
     int S = 0;
-    static constexpr int kSlots = 4;   // H2D of chunk i+1, kernel of chunk i and D2H of chunk i-1 in flight together (+1 slack)
+    static constexpr int kSlots = 6;   // H2D of chunk i+1, kernel of chunk i and D2H of chunk i-1 in flight together (+ slack: more chunks in flight keep both copy engines busy)
     cudaStream_t st[kSlots] = {};
     float *d_y[kSlots] = {};
     void *d_out[kSlots] = {};
