@@ -41,8 +41,25 @@ struct AcsParams {
     int64_t n_warp_tiles;
 };
 
+// path metrics in registers up to 64 states (32 distinct metrics + 32 new ones per frame), in shared memory beyond
+constexpr int kRegTrellisMaxL = 6;
 template <int L>
-using TrellisFor = typename std::conditional<(L <= 5), RegTrellis<L>, SmemTrellis<L>>::type;
+using TrellisFor = typename std::conditional<(L <= kRegTrellisMaxL), RegTrellis<L>, SmemTrellis<L>>::type;
+
+// chunk c of a stage on either kind of trellis; for the register trellis c must fold to a constant (unrolled callers)
+template <int L>
+__device__ __forceinline__ uint32_t step_chunk_any(TrellisFor<L> &tr, int c, const float (&cc)[TrellisDims<L>::C]) {
+    if constexpr (L <= kRegTrellisMaxL) {
+        switch (c) {
+            case 0: return tr.template step_chunk<0>(cc);
+            case 1: return tr.template step_chunk<(TrellisDims<L>::NCH > 1 ? 1 : 0)>(cc);
+            case 2: return tr.template step_chunk<(TrellisDims<L>::NCH > 2 ? 2 : 0)>(cc);
+            default: return tr.template step_chunk<(TrellisDims<L>::NCH > 3 ? 3 : 0)>(cc);
+        }
+    } else {
+        return tr.step_chunk_rt(c, cc);
+    }
+}
 
 template <int L, int NT>
 __global__ void __launch_bounds__(NT, (L <= 5) ? 4 : 1) acs_decode_kernel(AcsParams p) {
@@ -56,7 +73,7 @@ __global__ void __launch_bounds__(NT, (L <= 5) ? 4 : 1) acs_decode_kernel(AcsPar
     const float *row = tile + lane * kTileLd;
 
     TrellisFor<L> tr;
-    if constexpr (L > 5) tr.init(smem + WARPS * kTileFloats, NT, threadIdx.x);
+    if constexpr (L > kRegTrellisMaxL) tr.init(smem + WARPS * kTileFloats, NT, threadIdx.x);
 
     const int64_t ld = int64_t(p.T) * S;
     const bool vec_in = is_vec_ok(p.cost, ld, ld);
@@ -99,6 +116,7 @@ __global__ void __launch_bounds__(NT, (L <= 5) ? 4 : 1) acs_decode_kernel(AcsPar
                     constexpr int TPS = S / 32;  // staged tiles per stage
                     bits |= tr.decide() << tt;
                     uint32_t sv = 0;
+#pragma unroll(L <= kRegTrellisMaxL ? TPS : 1)
                     for (int k = 0; k < TPS; k++) {
                         warp_load_tile(p.cost, p.B, ld, ld, row0, int64_t(t0 + tt) * S + 32 * k, tile, lane, vec_in);
 #pragma unroll
@@ -107,7 +125,7 @@ __global__ void __launch_bounds__(NT, (L <= 5) ? 4 : 1) acs_decode_kernel(AcsPar
 #pragma unroll
                             for (int i = 0; i < C; i++) cc[i] = row[u * C + i];
                             const int c = 2 * k + u;
-                            const uint32_t s8 = tr.step_chunk_rt(c, cc);
+                            const uint32_t s8 = step_chunk_any<L>(tr, c, cc);
                             sv |= s8 << ((c * 8) & 31);
                             if ((c & 3) == 3 || c == NCH - 1) {
                                 if (p.survivors && b < p.B)
@@ -178,7 +196,7 @@ __global__ void __launch_bounds__(NT, (L <= 5) ? 4 : 1) va_decode_kernel(VaParam
     constexpr bool PACKED = (L >= 2 && L <= 5);
     using Tr = typename std::conditional<PACKED, PackedTrellis<PACKED ? L : 2>, TrellisFor<L>>::type;
     Tr tr;
-    if constexpr (L > 5) tr.init(smem + WARPS * 2 * kTileFloats, NT, threadIdx.x);
+    if constexpr (L > kRegTrellisMaxL) tr.init(smem + WARPS * 2 * kTileFloats, NT, threadIdx.x);
 
     const bool vec_in = is_vec_ok(p.y, p.T, p.T);
     const bool vec_out = p.out_format == MVN_OUT_F32 && is_vec_ok(p.decoded, p.T, p.T);
@@ -234,6 +252,7 @@ __global__ void __launch_bounds__(NT, (L <= 5) ? 4 : 1) va_decode_kernel(VaParam
                             tr.template step_chunk<1>(c1);
                         }
                     } else {
+#pragma unroll(L <= kRegTrellisMaxL ? NCH : 1)
                         for (int c = 0; c < NCH; c++) {
                             float cc[C];
 #pragma unroll
@@ -244,7 +263,7 @@ __global__ void __launch_bounds__(NT, (L <= 5) ? 4 : 1) va_decode_kernel(VaParam
                                 cc[i + 2] = va_cost(yv, s4.z);
                                 cc[i + 3] = va_cost(yv, s4.w);
                             }
-                            tr.step_chunk_rt(c, cc);
+                            step_chunk_any<L>(tr, c, cc);
                         }
                     }
                     if constexpr (!PACKED) tr.commit();
@@ -283,7 +302,7 @@ template <int L>
 static int launch_acs(const AcsParams &p, cudaStream_t st) {
     constexpr int NT = (L <= 5) ? 256 : 128;
     size_t smem = size_t(NT / 32) * kTileFloats * sizeof(float);
-    if (L > 5) smem += SmemTrellis<L>::bytes(NT);
+    if (L > kRegTrellisMaxL) smem += SmemTrellis<L>::bytes(NT);
     auto kern = acs_decode_kernel<L, NT>;
     MVN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     int per_sm = 1;
@@ -301,7 +320,7 @@ template <int L>
 static int launch_va(const VaParams &p, cudaStream_t st) {
     constexpr int NT = (L <= 5) ? 256 : 128;
     size_t smem = size_t(NT / 32) * 2 * kTileFloats * sizeof(float);
-    if (L > 5) smem += SmemTrellis<L>::bytes(NT);
+    if (L > kRegTrellisMaxL) smem += SmemTrellis<L>::bytes(NT);
     auto kern = va_decode_kernel<L, NT>;
     MVN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     int per_sm = 1;
