@@ -3,7 +3,9 @@
 METAVNETTrainer.eval_by_word (trainers/trainer.py:267-354) with self-supervised online training
 (metavnet_trainer.py:52-64), online_meta off, on a short sequence of RS-coded words over a fading ISI channel.
 
-    python tests/golden/make_golden_online.py
+    python tests/golden/make_golden_online.py            # online.npz: runs a, b, m, n (time_decay taps)
+    python tests/golden/make_golden_online.py cost2100   # online_cost2100.npz: runs c, d on the COST2100 taps
+                                                         # (BASELINE.json configs[3]; channel_estimation.py:26-30)
 
 Recorded: the words the reference's dataset drew (information bits, channel outputs), the detector weights before the
 run (after a short supervised warm-up so that detection mostly works), the SER per word the reference returns and the
@@ -26,15 +28,20 @@ def main():
     from python_code.trainers.META_VNET.metavnet_trainer import METAVNETTrainer
     from python_code.ecc.rs_main import encode
     out = {}
+    cost = len(sys.argv) > 1 and sys.argv[1] == 'cost2100'
+    runs = ((('c', 10.0, False, False), ('d', 10.0, False, True)) if cost else
+            (('a', 9.0, True, False), ('b', 6.0, False, False), ('m', 9.0, True, True), ('n', 7.0, True, True)))
     with tempfile.TemporaryDirectory() as tmp:
-        for tag, snr, fading, meta in (('a', 9.0, True, False), ('b', 6.0, False, False), ('m', 9.0, True, True),
-                                       ('n', 7.0, True, True)):
+        if cost:
+            import python_code.channel.channel_estimation as ce
+            ce.COST2100_DIR = mg._cost2100_dir(tmp)
+        for tag, snr, fading, meta in runs:
             wd = os.path.join(tmp, f'w_online_{tag}')
             os.makedirs(wd, exist_ok=True)
             torch.manual_seed(21)
             tr = METAVNETTrainer(memory_length=4, use_ecc=True, n_symbols=2, val_frames=3, subframes_in_frame=4,
                                  train_frames=1, val_block_length=120, fading_in_channel=fading, fading_in_decoder=False,
-                                 channel_coefficients='time_decay', self_supervised=True, self_supervised_iterations=4,
+                                 channel_coefficients='cost2100' if cost else 'time_decay', self_supervised=True, self_supervised_iterations=4,
                                  ser_thresh=0.02 if tag != 'n' else 0.05, online_meta=meta, buffer_empty=True, lr=1e-3,
                                  weights_dir=wd, eval_mode='by_word', meta_subframes=4, meta_train_iterations=2,
                                  meta_j_num=3, window_size=1, MAML=(tag != 'n'), meta_lr=0.1, weights_init='last_frame')
@@ -95,7 +102,7 @@ def main():
             out[f'{tag}_meta_cfg'] = np.array([int(meta), tr.meta_subframes, tr.meta_train_iterations, tr.meta_j_num,
                                                tr.window_size, int(tr.MAML), tr.meta_lr])
             print(tag, 'ser by word', ser, 'trained after', len(after), 'blocks')
-    mg.save('online', **out)
+    mg.save('online_cost2100' if cost else 'online', **out)
 
 
 if __name__ == '__main__':

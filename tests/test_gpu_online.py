@@ -178,3 +178,25 @@ def test_online_meta_with_initial_sliding_buffer_and_wider_window(mvn):
                             second_order=False, init_buffer=(init_tx, rx[:, :5]), draw=lambda run, high, count: [1],
                             weights_init=lambda runs: (calls.append(list(runs)) or fresh[runs]))
     assert calls == [[0, 1]] and tr2.adam_step.tolist() == [1, 1]      # one round at word 4: restart, then one step
+
+
+def test_online_evaluation_replays_cost2100_runs(mvn):
+    """BASELINE.json configs[3]: the same replay on the COST2100 taps (tests/golden/online_cost2100.npz, recorded from
+    METAVNETTrainer.eval_by_word with channel_coefficients='cost2100', channel_estimation.py:26-30): run c is
+    self-supervised only, run d adds online meta-training (MAML) with the reference's torch.randint draws."""
+    g = load_golden('online_cost2100')
+    ser, after = run(mvn, g, ('c',))
+    assert np.max(np.abs(ser[0] - g['c_ser'])) < 1e-7
+    assert len(after[0]) == len(g['c_theta_after'])
+    for got, want in zip(after[0], g['c_theta_after']):
+        assert np.max(np.abs(got - want)) < 2e-5
+    torch.manual_seed(int(g['d_seed'][0]))
+    drawn = []
+
+    def draw(run_, high, count):
+        out = mvn.online._default_draw(run_, high, count)
+        drawn.extend(out)
+        return out
+    ser, after, meta_after = run_meta(mvn, g, ('d',), draw)
+    assert drawn == g['d_jhat'].tolist()
+    check_meta(g, ('d',), ser, after, meta_after)

@@ -201,21 +201,7 @@ def test_vnet_priors_tiny_trellis(mvn, L):
 
 
 # ------------------------------------------------------------------------------- a6+a3 fused
-def _explain_mismatches(dec_k, dec_ref, priors_ref, tol_rows):
-    """Every frame whose bits differ from the reference must differ first at a stage where, under
-    the reference's priors, the best and runner-up metrics of different parity are closer than the
-    accumulated prior tolerance."""
-    bad = np.nonzero((dec_k != dec_ref).any(axis=1))[0]
-    for b in bad:
-        t = int(np.nonzero(dec_k[b] != dec_ref[b])[0][0])
-        cost = -priors_ref[b:b + 1].astype(np.float32)
-        _, pm = orc.acs_decode(cost[:, :t], t)          # metrics entering stage t
-        H = pm.shape[1] // 2
-        v = pm[0, :H]
-        even, odd = v[0::2].min(), v[1::2].min()
-        gap = abs(float(even) - float(odd))
-        assert gap <= 2 * t * tol_rows[b], f'frame {b} stage {t}: gap {gap} not a near-tie'
-    return len(bad)
+from parity_utils import explain_mismatches as _explain_mismatches, unpack_rows  # noqa: E402
 
 
 @pytest.mark.parametrize('tag', ['init', 'trained'])
@@ -433,6 +419,90 @@ def test_full_size_properties(mvn, fused_impl):
     assert torch.equal(mvn.ops.unpack_bits(words[:5000], T), dec_big[:5000])
 
 
+# ------------------------------------------------------------------------------- protocol (ii) at real sizes
+def test_vnet_4100_frames_against_reference_forward(mvn, fused_impl):
+    """4 100 words decoded by the reference's full VNETDetector.forward (tests/golden/vnet4096.npz, reference-trained
+    weights): every frame a kernel variant decodes differently must be explained as a near-tie under fp64 priors."""
+    g, v = load_golden('vnet4096'), load_golden('vnet')
+    w, y, T = _w(v, 'trained_w'), g['y'], int(g['T'][0])
+    ref = unpack_rows(g['dec_packed'], T)
+    dec, pri = mvn.ops.vnet_decode(cu(y), [cu(a) for a in w], return_priors=True)
+    dec, pri = dec.cpu().numpy(), pri.cpu().numpy()
+    exact = orc.vnet_priors(y, w, dtype=np.float64)
+    assert rel_to_rowmax(pri, exact) < PRIOR_RTOL
+    own, _ = orc.vnet_decode_from_priors(pri)
+    assert np.array_equal(dec, own)                                                   # protocol (i)
+    tol = PRIOR_RTOL * np.abs(exact).max(axis=(1, 2))
+    assert _explain_mismatches(dec, ref, exact, tol) <= 2                             # protocol (ii)
+
+
+def test_tensor_core_vs_fma_disagreements_are_near_ties(mvn):
+    """2^18 frames with an UNTRAINED net (small margins, the worst case: tools/stress_tc.py saw 244 differing frames per
+    2^20): every frame on which the tcgen05 kernel and the FP32-FMA kernel disagree must be a near-tie under fp64
+    priors, and both must follow their own priors exactly on those frames."""
+    torch.manual_seed(4)
+    net = torch.nn.Sequential(torch.nn.Linear(1, 100), torch.nn.Sigmoid(), torch.nn.Linear(100, 50), torch.nn.ReLU(),
+                              torch.nn.Linear(50, 16))
+    w = [p.detach().cuda().contiguous() for p in net.parameters()]
+    w_np = [a.cpu().numpy() for a in w]
+    rng = np.random.RandomState(11)
+    B, T, L = 1 << 18, 120, 4
+    bits = torch.randint(0, 2, (B, T), generator=torch.Generator().manual_seed(3)).float()
+    h = np.exp(-0.2 * np.arange(L)).reshape(1, L)
+    y = mvn.ops.channel_transmit(bits.cuda(), h, 9.0, seed=17)
+    out = {}
+    for name in ('tcgen05', 'fma'):
+        mvn.ops.set_fused_variant(name)
+        try:
+            out[name] = mvn.ops.vnet_decode(y, w)
+        finally:
+            mvn.ops.set_fused_variant('auto')
+    bad = torch.nonzero((out['tcgen05'] != out['fma']).any(dim=1)).reshape(-1).cpu().numpy()
+    assert len(bad) < B // 1000
+    if len(bad):
+        yb = y[bad].cpu().numpy()
+        exact = orc.vnet_priors(yb, w_np, dtype=np.float64)
+        tol = PRIOR_RTOL * np.abs(exact).max(axis=(1, 2))
+        n = _explain_mismatches(out['tcgen05'][bad].cpu().numpy(), out['fma'][bad].cpu().numpy(), exact, tol)
+        assert n == len(bad)
+        for name in ('tcgen05', 'fma'):           # each variant is exact on its own priors for exactly these frames
+            mvn.ops.set_fused_variant(name)
+            try:
+                d, p = mvn.ops.vnet_decode(cu(yb), w, return_priors=True)
+            finally:
+                mvn.ops.set_fused_variant('auto')
+            assert np.array_equal(d.cpu().numpy(), orc.vnet_decode_from_priors(p.cpu().numpy())[0])
+            assert np.array_equal(d.cpu().numpy(), out[name][bad].cpu().numpy())      # batch position does not matter
+
+
+@pytest.mark.parametrize('tag', ['raw', 'ecc'])
+def test_config1_300_blocks(mvn, tag):
+    """BASELINE.json configs[0] at its real size through the drop-in classes: 300 blocks (val_frames=12), fading taps,
+    10 dB; VA bit-exact, ViterbiNet by protocol (ii), the reference's SER / FER on the data rows (RS-decoded on the GPU
+    when coded) reproduced as identical floats."""
+    g, v = load_golden('config1'), load_golden('vnet')
+    y, b = g[f'{tag}_y'], g[f'{tag}_b'].astype(np.float32)
+    T = y.shape[1]
+    va = mvn.VADetector(16, 4, T, 300, 'ISI_AWGN', 0, True, 1, {'train': 'time_decay', 'val': 'time_decay'})
+    dec_va = va(cu(y), 'val', 10.0, 0.2)
+    assert np.array_equal(dec_va.cpu().numpy(), unpack_rows(g[f'{tag}_dec_va'], T))
+    det = mvn.VNETDetector(16, {'val': T, 'train': T})
+    with torch.no_grad():
+        for p, a in zip(det.parameters(), _w(v, 'trained_w')):
+            p.copy_(cu(a))
+    dec_vn = det(cu(y), 'val')
+    ref_vn = unpack_rows(g[f'{tag}_dec_vnet'], T)
+    exact = orc.vnet_priors(y, _w(v, 'trained_w'), dtype=np.float64)
+    assert _explain_mismatches(dec_vn.cpu().numpy(), ref_vn, exact, PRIOR_RTOL * np.abs(exact).max(axis=(1, 2))) <= 1
+    assert rel_to_rowmax(det(cu(y[:25]), 'train').detach().cpu().numpy(), g[f'{tag}_priors25']) < PRIOR_RTOL
+    rows = torch.as_tensor(g[f'{tag}_data_indices']).cuda()
+    for nm, d in (('va', dec_va), ('vnet', cu(ref_vn))):
+        msg = mvn.ecc.decode(d, 2) if tag == 'ecc' else d
+        ber, fer, idx = mvn.calculate_error_rates(msg[rows], cu(b)[rows])
+        assert ber == g[f'{tag}_rates_{nm}'][0] and fer == g[f'{tag}_rates_{nm}'][1]
+        assert np.array_equal(idx.cpu().numpy(), g[f'{tag}_erridx_{nm}'])
+
+
 # ------------------------------------------------------------------------------- shared state / sweeps
 def test_constant_slots_are_safe_across_streams(mvn, fused_impl):
     """The fused kernel keeps its weights in two constant-bank slots; interleaved calls with DIFFERENT
@@ -487,27 +557,30 @@ def test_sweep_on_gpu_counts(mvn):
 
 
 # ------------------------------------------------------------------------------- SURVEY.md §8(f) next rows
-@pytest.mark.parametrize('L', [3, 4, 6])
-def test_channel_transmit_matches_reference_channel(mvn, L):
+@pytest.mark.parametrize('name', ['static_ecc', 'fade1', 'fade2_ecc', 'cost2100', 'L6_static'])
+def test_channel_transmit_matches_reference_draw(mvn, name):
+    """f1 pinned: mvn_channel_transmit fed the recorded RandomState(noise_seed) stream reproduces the words a
+    ChannelModelDataset draw of the live reference produced (tests/golden/channel.npz, make_golden_r2.py) bit for bit."""
+    g = load_golden('channel')
+    L, T, snr = int(g[f'{name}_meta'][0]), int(g[f'{name}_meta'][1]), float(g[f'{name}_meta'][2])
+    y = mvn.ops.channel_transmit(cu(g[f'{name}_c'].astype(np.float32)), g[f'{name}_h'], snr, noise=g[f'{name}_noise'])
+    assert np.array_equal(y.cpu().numpy().view(np.uint32), g[f'{name}_y'].view(np.uint32))
+
+
+@pytest.mark.parametrize('L', [1, 2, 4, 6, 8])
+def test_channel_transmit_matches_oracle(mvn, L):
+    """other memory lengths / per-word random taps: against the oracle (itself pinned on the reference draw above)"""
     rng = np.random.RandomState(L)
     B, T = 37, 136
     bits = rng.randint(0, 2, size=(B, T))
     h = np.abs(rng.randn(B, L)) + 0.1                      # one tap vector per word (fading)
-    noise = rng.normal(0, 1, (B, T))
-    ref = np.zeros((B, T))
-    c = np.concatenate([bits, np.zeros((B, L))], axis=1)
-    s = 1 - 2 * c
-    for i in range(L):
-        ref += h[:, L - 1 - i:L - i] * s[:, i:i + T]
-    ref = (ref + (10 ** (9.0 / 10)) ** (-0.5) * noise).astype(np.float32)
+    noise = np.random.RandomState(100 + L).normal(0, 1, (B, T))
+    ref = orc.isi_awgn(bits, h, 9.0, L, np.random.RandomState(100 + L)).astype(np.float32)
     y = mvn.ops.channel_transmit(cu(bits.astype(np.float32)), h, 9.0, noise=noise)
     assert np.array_equal(y.cpu().numpy(), ref)
-    # static channel (one tap row) through the oracle's restatement
-    rng2 = np.random.RandomState(7)
-    h1 = np.exp(-0.2 * np.arange(L)).reshape(1, L)
-    n2 = rng2.normal(0, 1, (B, T))
-    ref2 = orc.isi_awgn(bits, h1, 10.0, L, np.random.RandomState(7)).astype(np.float32)
-    y2 = mvn.ops.channel_transmit(cu(bits.astype(np.float32)), h1, 10.0, noise=n2)
+    h1 = np.exp(-0.2 * np.arange(L)).reshape(1, L)         # static channel (one tap row)
+    ref2 = orc.isi_awgn(bits, h1, 10.0, L, np.random.RandomState(100 + L)).astype(np.float32)
+    y2 = mvn.ops.channel_transmit(cu(bits.astype(np.float32)), h1, 10.0, noise=noise)
     assert np.array_equal(y2.cpu().numpy(), ref2)
 
 

@@ -195,3 +195,86 @@ def test_mlse_traceback_is_the_minimum_cost_path(L):
     dec0, states0, _ = orc.mlse_decode(cost, start_state=0)
     assert np.all(states0[:, -1] == 0)
     assert np.array_equal(orc.path_cost(cost, states0), pm[:, 0])
+
+
+CHANNEL_CASES = ['static_ecc', 'fade1', 'fade2_ecc', 'cost2100', 'L6_static']
+
+
+@pytest.mark.parametrize('name', CHANNEL_CASES)
+def test_channel_simulator_pinned_on_reference_draw(name):
+    """f1: orc.isi_awgn fed the reference's own RandomState(noise_seed) stream reproduces a recorded
+    ChannelModelDataset draw (channel.py:12-35, channel_dataset.py:55-95): the fp32 words the dataset hands to the
+    detectors bit for bit, and the float64 pre-cast values too at memory_length 4 (at L=6 numpy's BLAS dot sums the six
+    taps in another order than the restatement: 1 ulp of float64, invisible after the fp32 cast)."""
+    g = load_golden('channel')
+    L, T, snr, gamma, noise_seed, _ = g[f'{name}_meta']
+    L = int(L)
+    c, h = g[f'{name}_c'].astype(np.float64), g[f'{name}_h']
+    assert c.shape[1] == int(T)
+    rng = np.random.RandomState(int(noise_seed))
+    y = np.concatenate([orc.isi_awgn(c[i:i + 1], h[i:i + 1], snr, L, rng) for i in range(c.shape[0])])  # one draw per word
+    assert np.array_equal(y.astype(np.float32).view(np.uint32), g[f'{name}_y'].view(np.uint32))
+    if L == 4:
+        assert np.array_equal(y, g[f'{name}_y64'])
+    else:
+        assert np.max(np.abs(y - g[f'{name}_y64'])) <= 2 ** -50
+    # the recorded noise IS that stream, and the taps are the restated estimate_channel
+    assert np.array_equal(np.random.RandomState(int(noise_seed)).normal(0, 1, g[f'{name}_noise'].shape), g[f'{name}_noise'])
+    if name != 'cost2100':
+        kw = {'fade1': dict(fading=True, fading_taps_type=1), 'fade2_ecc': dict(fading=True, fading_taps_type=2)}.get(name, {})
+        mine = np.concatenate([orc.estimate_channel(L, gamma, 'time_decay', index=i, **kw) for i in range(h.shape[0])])
+        assert np.array_equal(mine, h)
+
+
+def test_vnet_4100_frames_full_forward_protocol():
+    """Protocol (ii) of SURVEY.md §8c at a real sample size: 4 100 words decoded by the reference's full
+    VNETDetector.forward (reference-trained weights); every frame the oracle decodes differently must be a near-tie."""
+    from parity_utils import explain_mismatches, unpack_rows, PRIOR_RTOL
+    g, v = load_golden('vnet4096'), load_golden('vnet')
+    w, y, T = _w(v, 'trained_w'), g['y'], int(g['T'][0])
+    ref = unpack_rows(g['dec_packed'], T)
+    dec = orc.vnet_decode(y, w)
+    exact = lambda rows: orc.vnet_priors(y[rows], w, dtype=np.float64)
+    tol = PRIOR_RTOL * 40.0 * np.ones(y.shape[0])       # priors of the trained net reach |p| ~ 40
+    assert explain_mismatches(dec, ref, exact, tol) <= 2
+
+
+@pytest.mark.parametrize('tag', ['raw', 'ecc'])
+def test_config1_300_blocks(tag):
+    """BASELINE.json configs[0] at its real size (val_frames=12 -> 300 blocks, fading taps, 10 dB): VA bit-exact,
+    ViterbiNet by protocol (ii), and the reference's SER / FER on the data rows (RS-decoded when coded)."""
+    from oracle import rs_oracle
+    from parity_utils import explain_mismatches, unpack_rows, PRIOR_RTOL
+    g, v = load_golden('config1'), load_golden('vnet')
+    y, h, b = g[f'{tag}_y'], g[f'{tag}_h'], g[f'{tag}_b'].astype(np.float32)
+    T = y.shape[1]
+    assert y.shape[0] == 300
+    dec_va = orc.va_decode(y, h, 4, T)
+    assert np.array_equal(dec_va, unpack_rows(g[f'{tag}_dec_va'], T))
+    w = _w(v, 'trained_w')
+    ref_vn = unpack_rows(g[f'{tag}_dec_vnet'], T)
+    pri = orc.vnet_priors(y, w)
+    assert _rel_to_rowmax(pri[:25], g[f'{tag}_priors25']) < 1e-5
+    dec_vn, _ = orc.vnet_decode_from_priors(pri)
+    exact = lambda rows: orc.vnet_priors(y[rows], w, dtype=np.float64)
+    assert explain_mismatches(dec_vn, ref_vn, exact, PRIOR_RTOL * 40.0 * np.ones(300)) <= 1
+    rows = g[f'{tag}_data_indices']
+    for nm, d in (('va', dec_va), ('vnet', ref_vn)):
+        msg = np.stack([rs_oracle.decode(wd.astype(int), 2) for wd in d]).astype(np.float32) if tag == 'ecc' else d
+        ber, fer, idx = orc.calculate_error_rates(msg[rows], b[rows])
+        assert ber == g[f'{tag}_rates_{nm}'][0] and fer == g[f'{tag}_rates_{nm}'][1]
+        assert np.array_equal(idx, g[f'{tag}_erridx_{nm}'])
+
+
+def test_reference_trained_checkpoints_decode_sanely():
+    """the checkpoints bench.py decodes with (reference VNETTrainer.train() per SNR): oracle BER on a fresh synthetic
+    draw is in the range the reference reported for them"""
+    g = load_golden('ckpt_vnet_L4')
+    rng = np.random.RandomState(5)
+    bits = rng.randint(0, 2, size=(400, 120))
+    h = np.exp(-0.2 * np.arange(4)).reshape(1, 4)
+    for snr in (7, 10, 12):
+        w = [g[f'snr{snr}_w{i}'] for i in range(6)]
+        y = orc.isi_awgn(bits, h, float(snr), 4, rng).astype(np.float32)
+        ber = float((orc.vnet_decode(y, w) != bits)[:, 1:].mean())
+        assert 0.3 * g[f'snr{snr}_ser'][0] < ber < 3 * g[f'snr{snr}_ser'][0], (snr, ber)
