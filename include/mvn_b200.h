@@ -9,7 +9,11 @@
  * Conventions
  *   - All pointers are DEVICE pointers unless the name ends in `_host`.  fp32 = IEEE binary32,
  *     tensors contiguous row-major.  `stream` is a cudaStream_t passed as void* (NULL = default).
- *   - Calls are asynchronous on `stream`, allocate nothing, and keep no global state.
+ *   - Calls are asynchronous on `stream` and allocate no device memory.  Library state shared between calls is
+ *     limited to: (1) the pair of constant-bank weight slots of the FP32-FMA variants (handed over between streams
+ *     with events), (2) the tcgen05 pipeline-watchdog word per device (mvn_tc_timeout_status / mvn_reset_tc_timeout),
+ *     (3) lazily created CUDA events for (1).  Which kernel variant runs is a per-call / per-context argument,
+ *     never a process-wide switch.  Thread-compatible: concurrent calls from several host threads are safe.
  *   - Return 0 on success, non-zero MVN_ERR_* otherwise; mvn_last_error() describes the last
  *     failure of the calling thread.
  *   - memory_length L in [1,8] (n_states S = 2^L); the trellis is the reference's:
@@ -39,6 +43,18 @@ extern "C" {
 /* Output formats for decoded bits. */
 #define MVN_OUT_F32 0       /* [B,T] fp32 0.0/1.0 — the reference's dtype                     */
 #define MVN_OUT_BITS 1      /* [B,ceil(T/32)] uint32, bit (t%32) of word t/32 = decoded[b,t]  */
+
+/* Implementation of the fused ViterbiNet kernel (argument `variant` of mvn_vnet_decode_ex / mvn_ctx_set_variant). */
+#define MVN_VARIANT_AUTO 0          /* library default: tcgen05 tensor cores for every memory_length */
+#define MVN_VARIANT_FMA_SMEM 1      /* FP32 FMA pipe, weights staged in shared memory              */
+#define MVN_VARIANT_FMA_CONST320 2  /* FP32 FMA pipe, constant-bank weights, 320 threads (tuning)  */
+#define MVN_VARIANT_TCGEN05 3       /* tensor cores explicitly                                     */
+#define MVN_VARIANT_FMA 4           /* FP32 FMA pipe, constant-bank weights (default FMA form)     */
+
+/* Decision rule (argument `decision` of the *_ex entry points). */
+#define MVN_DECIDE_REFERENCE 0      /* the reference's rule: bit t = (lowest argmin of pm) & 1 BEFORE stage t's ACS  */
+#define MVN_DECIDE_MLSE 1           /* true MLSE: in-kernel survivor traceback from the best final state             */
+#define MVN_DECIDE_MLSE_TERMINATED 2 /* traceback from state 0 (the reference pads every word with L zero bits)      */
 
 const char *mvn_last_error(void);
 int mvn_version(void);
@@ -76,6 +92,13 @@ int mvn_va_decode(const float *y, int64_t B, int T, int L, int n_stages, const f
                   int n_h, int out_format, void *decoded, const float *target, int target_T,
                   int pilot_period, uint64_t *counters, void *stream);
 
+/* Same with the decision rule selectable: MVN_DECIDE_MLSE* keep the S/2 survivor bits of every stage
+ * (trellis_utils.py:30's indices, which the reference discards) as bit masks in shared memory and trace back inside
+ * the kernel at the end of the frame — nothing but y and the decoded bits touches HBM (8 B per symbol). */
+int mvn_va_decode_ex(const float *y, int64_t B, int T, int L, int n_stages, const float *state_priors, int n_h,
+                     int out_format, void *decoded, const float *target, int target_T, int pilot_period,
+                     uint64_t *counters, int decision, void *stream);
+
 /* ---- a6: ViterbiNet priors.  Replaces VNETDetector.net / META_VNETDetector's F.linear chain
  * (vnet_detector.py:27-33,49; meta_vnet_detector.py:27-33).  Weights in torch nn.Linear layout:
  * w1 [100,1], b1 [100], w2 [50,100], b2 [50], w3 [S,50], b3 [S].  y flattened [N]; priors [N,S]. */
@@ -90,6 +113,17 @@ int mvn_vnet_decode(const float *y, int64_t B, int T, int L, int n_stages, const
                     const float *w2, const float *b2, const float *w3, const float *b3, int out_format,
                     void *decoded, float *priors_out, const float *target, int target_T, int pilot_period,
                     uint64_t *counters, void *stream);
+
+/* Same with the kernel variant (MVN_VARIANT_*) and the decision rule (MVN_DECIDE_*) chosen per call. */
+int mvn_vnet_decode_ex(const float *y, int64_t B, int T, int L, int n_stages, const float *w1, const float *b1,
+                       const float *w2, const float *b2, const float *w3, const float *b3, int out_format,
+                       void *decoded, float *priors_out, const float *target, int target_T, int pilot_period,
+                       uint64_t *counters, int variant, int decision, void *stream);
+/* tcgen05 pipeline watchdog of the current device: status = 1 if an mbarrier wait of the tensor-core kernel gave up
+ * (2 s of wall clock; never expected) since the last reset; such a launch's output is invalid and further tcgen05
+ * launches on that device are refused until mvn_reset_tc_timeout(). */
+int mvn_tc_timeout_status(void);
+int mvn_reset_tc_timeout(void);
 
 /* ---- a8: ground-truth state labels.  Replaces trellis_utils.py:33-46 (calculate_states).
  * tx [B,T] fp32 0/1 -> states [B*T] int64, state[b,t] = sum_{i<L} tx[b,t+i] 2^i (zero past T). */
@@ -116,6 +150,30 @@ int mvn_ctx_vnet_decode_host(mvn_ctx *ctx, const float *y_host, int64_t B, int T
                              int out_format, void *decoded_host);
 int mvn_ctx_va_decode_host(mvn_ctx *ctx, const float *y_host, int64_t B, int T, int n_stages,
                            const float *state_priors_host, int n_h, int out_format, void *decoded_host);
+/* kernel variant (MVN_VARIANT_*) and decision rule (MVN_DECIDE_*) used by this context's decode calls */
+int mvn_ctx_set_variant(mvn_ctx *ctx, int variant);
+int mvn_ctx_set_decision(mvn_ctx *ctx, int decision);
+/* Same pipeline with the error counters fused: target_host [B,target_T] fp32 words (the transmitted bits the
+ * reference's dataset returns next to y) are uploaded chunk by chunk next to y, BER / FER are counted in the decode
+ * kernel (metrics.py:7-17, pilot rows b % pilot_period == 0 skipped) and ONLY counters_host[4] (32 bytes) come back;
+ * decoded_host may be NULL (or a MVN_OUT_* buffer to also get the words). */
+int mvn_ctx_vnet_eval_host(mvn_ctx *ctx, const float *y_host, const float *target_host, int64_t B, int T, int n_stages,
+                           int target_T, int pilot_period, int out_format, void *decoded_host, uint64_t *counters_host);
+/* Monte-Carlo point evaluated entirely on the device (the sweep shape of trainer.py:222-241 / plotter_main.py:117-122
+ * at scale): Bernoulli(1/2) words and AWGN from Philox (seed), BPSK + ISI with taps_host [n_h,L] float64 (row b mod n_h)
+ * at snr_db (mvn_channel_transmit), fused ViterbiNet decode with in-kernel BER / FER; counters_host[4] is the only
+ * device->host traffic.  Frames are processed in the context's chunks. */
+int mvn_ctx_vnet_sweep_point(mvn_ctx *ctx, int64_t B, int T, int n_stages, const double *taps_host, int n_h,
+                             double snr_db, uint64_t seed, int pilot_period, uint64_t *counters_host);
+/* Pinned (page-locked) host buffers for the *_host entry points; write_combined != 0 allocates the buffer
+ * write-combined (fast for the device to read over PCIe, slow for the host to read back: inputs only). */
+int mvn_host_alloc(void **ptr, size_t bytes, int write_combined);
+int mvn_host_free(void *ptr);
+/* Measurement helper: raw pinned host <-> device copy rate of `device` with the same chunking and stream count as the
+ * pipeline above but no kernel (the e2e ceiling).  h2d / d2h: which directions run (both = concurrently);
+ * seconds = wall time of `reps` passes over `bytes`. */
+int mvn_copy_ceiling(int device, void *host_in, void *host_out, size_t bytes, size_t chunk_bytes, int h2d, int d2h,
+                     int reps, double *seconds);
 /* number of kernel launches issued by this library on this thread since the last reset
  * (bench.py's gpu_launches claim). */
 int64_t mvn_launch_count(int reset);

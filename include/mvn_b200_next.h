@@ -21,6 +21,10 @@ extern "C" {
 int mvn_channel_transmit(const float *bits, int64_t B, int T, int L, const double *taps, int n_h, double snr_db,
                          const double *noise, uint64_t seed, float *y, void *stream);
 
+/* Bernoulli(1/2) words [B,T] fp32 0/1 from Philox4x32-10 (the role of word_rand_gen.randint, channel_dataset.py:67, for
+ * Monte-Carlo runs generated on the device). */
+int mvn_random_bits(float *bits, int64_t B, int T, uint64_t seed, void *stream);
+
 /* ---- f3: true-MLSE decoding by survivor traceback.  survivors [B,n_stages,max(1,S/64)] uint32 and final_pm [B,S] are the
  * optional outputs of mvn_acs_decode (trellis_utils.py:30's indices, which the reference detectors discard).
  * start_state < 0: trace back from the best final state (lowest index on ties); >= 0: from that state (0 for the

@@ -5,7 +5,7 @@ call raises.  torch is used only for device memory and the current stream.
 """
 import ctypes
 import os
-from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_uint64, c_void_p, POINTER
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p, POINTER
 
 import torch
 
@@ -33,6 +33,12 @@ _PROTOS = {
     'mvn_vnet_priors': (c_int, [c_void_p, c_int64, c_int] + [c_void_p] * 6 + [c_void_p, c_void_p]),
     'mvn_vnet_decode': (c_int, [c_void_p, c_int64, c_int, c_int, c_int] + [c_void_p] * 6 +
                         [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    'mvn_va_decode_ex': (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                 c_int, c_int, c_void_p, c_int, c_void_p]),
+    'mvn_vnet_decode_ex': (c_int, [c_void_p, c_int64, c_int, c_int, c_int] + [c_void_p] * 6 +
+                           [c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
+    'mvn_tc_timeout_status': (c_int, []),
+    'mvn_reset_tc_timeout': (c_int, []),
     'mvn_calculate_states': (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
     'mvn_error_counts': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'mvn_ctx_create': (c_int, [POINTER(c_void_p), c_int, c_int64, c_int, c_int]),
@@ -40,10 +46,20 @@ _PROTOS = {
     'mvn_ctx_set_vnet_weights_host': (c_int, [c_void_p] * 7),
     'mvn_ctx_vnet_decode_host': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     'mvn_ctx_va_decode_host': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
+    'mvn_ctx_set_variant': (c_int, [c_void_p, c_int]),
+    'mvn_ctx_set_decision': (c_int, [c_void_p, c_int]),
+    'mvn_ctx_vnet_eval_host': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                       c_void_p]),
+    'mvn_ctx_vnet_sweep_point': (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_double, c_uint64, c_int,
+                                         c_void_p]),
+    'mvn_host_alloc': (c_int, [POINTER(c_void_p), c_size_t, c_int]),
+    'mvn_host_free': (c_int, [c_void_p]),
+    'mvn_copy_ceiling': (c_int, [c_int, c_void_p, c_void_p, c_size_t, c_size_t, c_int, c_int, c_int, POINTER(c_double)]),
     'mvn_launch_count': (c_int64, [c_int]),
     # include/mvn_b200_next.h
     'mvn_channel_transmit': (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_double, c_void_p, c_uint64,
                                      c_void_p, c_void_p]),
+    'mvn_random_bits': (c_int, [c_void_p, c_int64, c_int, c_uint64, c_void_p]),
     'mvn_traceback': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'mvn_va_cost': (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     'mvn_rs_decode': (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),

@@ -173,6 +173,8 @@ struct VaParams {
     int target_T, pilot_period;
     unsigned long long *counters;
     int64_t n_warp_tiles;
+    int decision;      // MVN_DECIDE_*
+    int surv_words;    // MLSE: survivor words per frame (SurvStore<L>::words(n_stages))
 };
 
 __device__ __forceinline__ float va_cost(float y, float sp) {
@@ -181,10 +183,10 @@ __device__ __forceinline__ float va_cost(float y, float sp) {
     return __fmaf_rn(sq, 0.5f, -kLogSqrt2Pi);
 }
 
-template <int L, int NT>
-__global__ void __launch_bounds__(NT, (L <= 5) ? 4 : 1) va_decode_kernel(VaParams p) {
+template <int L, int NT, bool MLSE>
+__global__ void __launch_bounds__(NT, (L <= 5 && !MLSE) ? 4 : 1) va_decode_kernel(VaParams p) {
     using D = TrellisDims<L>;
-    constexpr int S = D::S, C = D::C, NCH = D::NCH;
+    constexpr int S = D::S, H = D::H, C = D::C, NCH = D::NCH;
     constexpr int WARPS = NT / 32;
     constexpr bool SP_REGS = (S <= 32);
     extern __shared__ __align__(16) float smem[];
@@ -196,7 +198,13 @@ __global__ void __launch_bounds__(NT, (L <= 5) ? 4 : 1) va_decode_kernel(VaParam
     constexpr bool PACKED = (L >= 2 && L <= 5);
     using Tr = typename std::conditional<PACKED, PackedTrellis<PACKED ? L : 2>, TrellisFor<L>>::type;
     Tr tr;
-    if constexpr (L > kRegTrellisMaxL) tr.init(smem + WARPS * 2 * kTileFloats, NT, threadIdx.x);
+    float *after_tiles = smem + WARPS * 2 * kTileFloats;
+    if constexpr (L > kRegTrellisMaxL) {
+        tr.init(after_tiles, NT, threadIdx.x);
+        after_tiles += SmemTrellis<L>::bytes(NT) / sizeof(float);
+    }
+    SurvStore<L> surv;
+    if constexpr (MLSE) surv.init(reinterpret_cast<uint32_t *>(after_tiles) + size_t(warp) * p.surv_words * 32, lane);
 
     const bool vec_in = is_vec_ok(p.y, p.T, p.T);
     const bool vec_out = p.out_format == MVN_OUT_F32 && is_vec_ok(p.decoded, p.T, p.T);
@@ -219,57 +227,8 @@ __global__ void __launch_bounds__(NT, (L <= 5) ? 4 : 1) va_decode_kernel(VaParam
         }
         tr.reset();
         unsigned frame_bit_errs = 0;
-        for (int t0 = 0; t0 < p.T; t0 += 32) {
-            uint32_t bits = 0;
-            const int t_end = min(32, p.n_stages - t0);
-            if (t_end > 0) {
-                // (prefetching the next tile into registers was measured slower: 271 vs 300 G sym/s — the extra
-                //  32 registers cost a resident CTA and the kernel is issue-bound, not latency-bound)
-                warp_load_tile(p.y, p.B, p.T, p.T, row0, t0, tile, lane, vec_in);
-                for (int tt = 0; tt < t_end; tt++) {
-                    const float yv = row[tt];
-                    bits |= tr.decide() << tt;
-                    if constexpr (PACKED) {
-                        // d = y*1 + (-sp) (one rounding, == y - sp); sq = d*d; cost = sq*0.5 - ln sqrt(2 pi)
-                        const u64_t yy = pk2(yv, yv), one2 = pk2(1.f, 1.f), half2 = pk2(0.5f, 0.5f);
-                        const u64_t negk2 = pk2(-kLogSqrt2Pi, -kLogSqrt2Pi);
-                        u64_t cost2[S / 2];
-#pragma unroll
-                        for (int i = 0; i < S / 2; i++) {
-                            const u64_t d2 = fma2(yy, one2, nsp2[i]);
-                            cost2[i] = fma2(mul2(d2, d2), half2, negk2);
-                        }
-                        tr.step(cost2);
-                    } else if constexpr (SP_REGS) {
-                        float c0[C];
-#pragma unroll
-                        for (int i = 0; i < C; i++) c0[i] = va_cost(yv, sp[i]);
-                        tr.template step_chunk<0>(c0);
-                        if constexpr (NCH == 2) {
-                            float c1[C];
-#pragma unroll
-                            for (int i = 0; i < C; i++) c1[i] = va_cost(yv, sp[C + i]);
-                            tr.template step_chunk<1>(c1);
-                        }
-                    } else {
-#pragma unroll(L <= kRegTrellisMaxL ? NCH : 1)
-                        for (int c = 0; c < NCH; c++) {
-                            float cc[C];
-#pragma unroll
-                            for (int i = 0; i < C; i += 4) {
-                                const float4 s4 = __ldg(reinterpret_cast<const float4 *>(sp_row + c * C + i));
-                                cc[i] = va_cost(yv, s4.x);
-                                cc[i + 1] = va_cost(yv, s4.y);
-                                cc[i + 2] = va_cost(yv, s4.z);
-                                cc[i + 3] = va_cost(yv, s4.w);
-                            }
-                            step_chunk_any<L>(tr, c, cc);
-                        }
-                    }
-                    if constexpr (!PACKED) tr.commit();
-                }
-                __syncwarp();
-            }
+        // one tile of 32 decided bits: words out (full-line stores), optional BER against the staged target tile
+        auto emit = [&](int t0, uint32_t bits) {
             if (p.decoded) {
                 if (p.out_format == MVN_OUT_F32)
                     warp_store_bits_f32(static_cast<float *>(p.decoded), p.B, p.T, p.T, row0, t0, bits, lane, vec_out);
@@ -281,6 +240,78 @@ __global__ void __launch_bounds__(NT, (L <= 5) ? 4 : 1) va_decode_kernel(VaParam
                 frame_bit_errs += tile_bit_errors(ttile + lane * kTileLd, bits, p.target_T - t0);
                 __syncwarp();
             }
+        };
+        for (int t0 = 0; t0 < p.T; t0 += 32) {
+            uint32_t bits = 0;
+            const int t_end = min(32, p.n_stages - t0);
+            if (t_end > 0) {
+                // (prefetching the next tile into registers was measured slower: 271 vs 300 G sym/s — the extra
+                //  32 registers cost a resident CTA and the kernel is issue-bound, not latency-bound)
+                warp_load_tile(p.y, p.B, p.T, p.T, row0, t0, tile, lane, vec_in);
+                for (int tt = 0; tt < t_end; tt++) {
+                    const float yv = row[tt];
+                    const int t = t0 + tt;
+                    if constexpr (!MLSE) bits |= tr.decide() << tt;
+                    if constexpr (PACKED) {
+                        // d = y*1 + (-sp) (one rounding, == y - sp); sq = d*d; cost = sq*0.5 - ln sqrt(2 pi)
+                        const u64_t yy = pk2(yv, yv), one2 = pk2(1.f, 1.f), half2 = pk2(0.5f, 0.5f);
+                        const u64_t negk2 = pk2(-kLogSqrt2Pi, -kLogSqrt2Pi);
+                        u64_t cost2[S / 2];
+#pragma unroll
+                        for (int i = 0; i < S / 2; i++) {
+                            const u64_t d2 = fma2(yy, one2, nsp2[i]);
+                            cost2[i] = fma2(mul2(d2, d2), half2, negk2);
+                        }
+                        const uint32_t sv = tr.template step<MLSE>(cost2);
+                        if constexpr (MLSE) surv.put(t, sv, t == p.n_stages - 1);
+                    } else if constexpr (SP_REGS) {
+                        float c0[C];
+#pragma unroll
+                        for (int i = 0; i < C; i++) c0[i] = va_cost(yv, sp[i]);
+                        uint32_t sv = tr.template step_chunk<0>(c0);
+                        if constexpr (NCH == 2) {
+                            float c1[C];
+#pragma unroll
+                            for (int i = 0; i < C; i++) c1[i] = va_cost(yv, sp[C + i]);
+                            sv |= tr.template step_chunk<1>(c1) << (C / 2);
+                        }
+                        if constexpr (MLSE) surv.put(t, sv, t == p.n_stages - 1);
+                    } else {
+                        uint32_t sv = 0;
+#pragma unroll(L <= kRegTrellisMaxL ? NCH : 1)
+                        for (int c = 0; c < NCH; c++) {
+                            float cc[C];
+#pragma unroll
+                            for (int i = 0; i < C; i += 4) {
+                                const float4 s4 = __ldg(reinterpret_cast<const float4 *>(sp_row + c * C + i));
+                                cc[i] = va_cost(yv, s4.x);
+                                cc[i + 1] = va_cost(yv, s4.y);
+                                cc[i + 2] = va_cost(yv, s4.z);
+                                cc[i + 3] = va_cost(yv, s4.w);
+                            }
+                            const uint32_t s8 = step_chunk_any<L>(tr, c, cc);
+                            if constexpr (MLSE) {
+                                sv |= s8 << ((c * 8) & 31);
+                                if ((c & 3) == 3) {
+                                    if constexpr (H <= 32) surv.put(t, sv, t == p.n_stages - 1);
+                                    else surv.put_word(t, c >> 2, sv);
+                                    sv = 0;
+                                }
+                            }
+                        }
+                    }
+                    if constexpr (!PACKED) tr.commit();
+                }
+                __syncwarp();
+            }
+            if constexpr (!MLSE) emit(t0, bits);
+        }
+        if constexpr (MLSE) {
+            __syncwarp();
+            const int start = p.decision == MVN_DECIDE_MLSE_TERMINATED ? 0 : best_final_state<H>(tr);
+            for (int t0 = ((p.T - 1) / 32) * 32; t0 >= ((p.n_stages + 31) / 32) * 32; t0 -= 32) emit(t0, 0u);  // columns past the loop stay 0
+            traceback_frame<L>(surv, p.n_stages, start, [&](int tile_idx, uint32_t bits) { emit(tile_idx * 32, bits); });
+            __syncwarp();
         }
         if (p.target) {
             const bool counted = b < p.B && !(p.pilot_period > 0 && b % p.pilot_period == 0);
@@ -316,12 +347,23 @@ static int launch_acs(const AcsParams &p, cudaStream_t st) {
     return MVN_OK;
 }
 
-template <int L>
-static int launch_va(const VaParams &p, cudaStream_t st) {
-    constexpr int NT = (L <= 5) ? 256 : 128;
+template <int L, bool MLSE>
+static int launch_va_mode(VaParams p, cudaStream_t st) {
+    // MLSE at 128 / 256 states: the survivor masks (T x S/2 bits per frame) share the CTA's shared memory with the
+    // path metrics, so fewer frames are resident per CTA
+    constexpr int NT = (L <= 5) ? 256 : (MLSE && L == 7) ? 64 : (MLSE && L == 8) ? 32 : 128;
     size_t smem = size_t(NT / 32) * 2 * kTileFloats * sizeof(float);
     if (L > kRegTrellisMaxL) smem += SmemTrellis<L>::bytes(NT);
-    auto kern = va_decode_kernel<L, NT>;
+    if (MLSE) {
+        p.surv_words = SurvStore<L>::words(p.n_stages);
+        smem += size_t(NT / 32) * SurvStore<L>::bytes_per_warp(p.n_stages);
+        if (smem > 227 * 1024) {
+            set_error("mvn_va_decode (MLSE): %d stages of %d survivor bits do not fit the shared memory of one CTA", p.n_stages,
+                      SurvStore<L>::H);
+            return MVN_ERR_UNSUPPORTED;
+        }
+    }
+    auto kern = va_decode_kernel<L, NT, MLSE>;
     MVN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     int per_sm = 1;
     MVN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
@@ -332,6 +374,11 @@ static int launch_va(const VaParams &p, cudaStream_t st) {
     note_launch();
     MVN_CUDA(cudaGetLastError());
     return MVN_OK;
+}
+
+template <int L>
+static int launch_va(const VaParams &p, cudaStream_t st) {
+    return p.decision == MVN_DECIDE_REFERENCE ? launch_va_mode<L, false>(p, st) : launch_va_mode<L, true>(p, st);
 }
 
 #define MVN_DISPATCH_L(L, FN, ...)                                   \
@@ -391,16 +438,18 @@ extern "C" int mvn_acs_decode(const float *cost, int64_t B, int T, int L, int n_
     return acs_decode_impl(p, L, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int mvn_va_decode(const float *y, int64_t B, int T, int L, int n_stages, const float *state_priors,
-                             int n_h, int out_format, void *decoded, const float *target, int target_T,
-                             int pilot_period, uint64_t *counters, void *stream) {
+extern "C" int mvn_va_decode_ex(const float *y, int64_t B, int T, int L, int n_stages, const float *state_priors,
+                                int n_h, int out_format, void *decoded, const float *target, int target_T,
+                                int pilot_period, uint64_t *counters, int decision, void *stream) {
     if (L < 1 || L > 8) {
         set_error("memory_length %d outside [1,8]", L);
         return MVN_ERR_ARG;
     }
     if (B < 0 || T < 0 || n_stages < 0 || n_stages > T || !state_priors || n_h < 1 || (B > 0 && T > 0 && !y) ||
-        (out_format != MVN_OUT_F32 && out_format != MVN_OUT_BITS)) {
-        set_error("mvn_va_decode: bad argument (B=%lld T=%d n_stages=%d n_h=%d)", (long long)B, T, n_stages, n_h);
+        (out_format != MVN_OUT_F32 && out_format != MVN_OUT_BITS) || decision < MVN_DECIDE_REFERENCE ||
+        decision > MVN_DECIDE_MLSE_TERMINATED) {
+        set_error("mvn_va_decode: bad argument (B=%lld T=%d n_stages=%d n_h=%d decision=%d)", (long long)B, T, n_stages, n_h,
+                  decision);
         return MVN_ERR_ARG;
     }
     if (B % n_h != 0) {  // the reference's tiling of the table fails to broadcast (va_detector.py:64-66)
@@ -413,6 +462,13 @@ extern "C" int mvn_va_decode(const float *y, int64_t B, int T, int L, int n_stag
     }
     if (B == 0 || T == 0) return MVN_OK;
     VaParams p{y, B, T, n_stages, state_priors, n_h, out_format, decoded, target, target_T, pilot_period,
-               reinterpret_cast<unsigned long long *>(counters), (B + 31) / 32};
+               reinterpret_cast<unsigned long long *>(counters), (B + 31) / 32, decision, 0};
     return va_decode_impl(p, L, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mvn_va_decode(const float *y, int64_t B, int T, int L, int n_stages, const float *state_priors,
+                             int n_h, int out_format, void *decoded, const float *target, int target_T,
+                             int pilot_period, uint64_t *counters, void *stream) {
+    return mvn_va_decode_ex(y, B, T, L, n_stages, state_priors, n_h, out_format, decoded, target, target_T, pilot_period,
+                            counters, MVN_DECIDE_REFERENCE, stream);
 }

@@ -285,19 +285,113 @@ struct PackedTrellis {
         }
         return bit;
     }
-    // cost2[i] = packed branch costs of source states (2i, 2i+1), i < H
-    __device__ __forceinline__ void step(const u64_t (&cost2)[H]) {
+    // cost2[i] = packed branch costs of source states (2i, 2i+1), i < H.  SURV: also return the H survivor bits
+    // (bit i = 1 iff the odd predecessor 2i+1 won strictly; ties keep predecessor 2i like torch.min, trellis_utils.py:30)
+    template <bool SURV = false>
+    __device__ __forceinline__ uint32_t step(const u64_t (&cost2)[H]) {
         float nw[H];
+        uint32_t surv = 0;
 #pragma unroll
         for (int i = 0; i < H; i++) {
             float a, b;
             upk2(add2(pm2[i % HP], cost2[i]), a, b);
             nw[i] = fminf(a, b);
+            if (SURV) surv |= (b < a) ? (1u << i) : 0u;
         }
 #pragma unroll
         for (int i = 0; i < HP; i++) pm2[i] = pk2(nw[2 * i], nw[2 * i + 1]);
+        return surv;
+    }
+    __device__ __forceinline__ float metric(int h) const {
+        float v[H];
+#pragma unroll
+        for (int i = 0; i < HP; i++) upk2(pm2[i], v[2 * i], v[2 * i + 1]);
+        float r = v[0];
+#pragma unroll
+        for (int i = 1; i < H; i++) r = (i == h) ? v[i] : r;
+        return r;
     }
 };
+
+// ---------------------------------------------------------------- in-kernel survivor store + traceback (true MLSE)
+// The H = S/2 survivor bits of every stage (what acs_block returns as indices, trellis_utils.py:30, and the
+// reference's detectors discard) are kept per frame as bit masks in shared memory: a warp owns words[w][32 lanes]
+// (lane-contiguous: conflict-free), SPW stages per 32-bit word for H <= 32, H/32 words per stage above.  At the end of
+// the frame each lane walks its own masks backwards: state(t) = sum_i b[t+i] 2^i, the predecessor of j is
+// (2j + sigma) mod S and sigma IS the transmitted bit b[t].
+template <int L>
+struct SurvStore {
+    static constexpr int S = 1 << L, H = (S >= 2) ? S / 2 : 1;
+    static constexpr int SPW = (H <= 32) ? 32 / H : 1;   // stages per word
+    static constexpr int WPS = (H <= 32) ? 1 : H / 32;   // words per stage
+    __host__ __device__ static constexpr int words(int n_stages) {
+        return (H <= 32) ? (n_stages + SPW - 1) / SPW : n_stages * WPS;
+    }
+    __host__ __device__ static constexpr size_t bytes_per_warp(int n_stages) { return size_t(words(n_stages)) * 32 * sizeof(uint32_t); }
+    uint32_t *base;   // &words[0][lane]
+    uint32_t acc;
+    __device__ __forceinline__ void init(uint32_t *warp_words, int lane) {
+        base = warp_words + lane;
+        acc = 0;
+    }
+    // all H bits of stage t at once (H <= 32)
+    __device__ __forceinline__ void put(int t, uint32_t sv, bool last_stage) {
+        static_assert(H <= 32, "put(): whole-stage form");
+        if constexpr (SPW == 1) {
+            base[t * 32] = sv;
+        } else {
+            const int k = t % SPW;
+            acc |= sv << (k * H);
+            if (k == SPW - 1 || last_stage) {
+                base[(t / SPW) * 32] = acc;
+                acc = 0;
+            }
+        }
+    }
+    // word w of stage t (H > 32)
+    __device__ __forceinline__ void put_word(int t, int w, uint32_t bits) { base[(t * WPS + w) * 32] = bits; }
+    __device__ __forceinline__ uint32_t get(int t, int jj) const {
+        if constexpr (H <= 32) {
+            return (base[(t / SPW) * 32] >> ((t % SPW) * H + jj)) & 1u;
+        } else {
+            return (base[(t * WPS + (jj >> 5)) * 32] >> (jj & 31)) & 1u;
+        }
+    }
+};
+
+// Lane-private traceback over stages [0, n_stages): calls emit(tile, bits) (warp-uniform control flow) with the 32
+// decided bits of stages [32 tile, 32 tile + 32), highest tile first.
+template <int L, class Emit>
+__device__ __forceinline__ void traceback_frame(const SurvStore<L> &sv, int n_stages, int start_state, Emit emit) {
+    constexpr int S = 1 << L, H = SurvStore<L>::H;
+    int j = start_state;
+    uint32_t bits = 0;
+    for (int t = n_stages - 1; t >= 0; t--) {
+        const uint32_t sigma = sv.get(t, j & (H - 1));
+        j = (2 * j + int(sigma)) & (S - 1);
+        bits |= sigma << (t & 31);
+        if ((t & 31) == 0) {
+            emit(t >> 5, bits);
+            bits = 0;
+        }
+    }
+}
+
+// lowest state index attaining the minimum final metric (always < H: states j and j + H are identical)
+template <int H, class Tr>
+__device__ __forceinline__ int best_final_state(const Tr &tr) {
+    float best = tr.metric(0);
+    int j = 0;
+#pragma unroll(H <= 32 ? H : 8)
+    for (int h = 1; h < H; h++) {
+        const float v = tr.metric(h);
+        if (v < best) {
+            best = v;
+            j = h;
+        }
+    }
+    return j;
+}
 
 // ---------------------------------------------------------------- fused BER/FER accounting
 struct ErrAcc {

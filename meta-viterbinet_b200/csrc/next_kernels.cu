@@ -43,6 +43,34 @@ __global__ void channel_kernel(const float *__restrict__ bits, int64_t B, int T,
     y[idx] = float(conv + w);
 }
 
+// Bernoulli(1/2) words for the on-device Monte-Carlo source (the role of word_rand_gen.randint(0, 2, ...),
+// channel_dataset.py:67): one Philox4x32-10 call yields 128 bits = 128 consecutive symbols of the flattened [B*T] array.
+__global__ void random_bits_kernel(float *__restrict__ bits, int64_t n, unsigned long long seed) {
+    const int64_t g = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;   // group of 128 symbols
+    if (g * 128 >= n) return;
+    curandStatePhilox4_32_10_t st;
+    curand_init(seed, (unsigned long long)g, 0, &st);
+    const uint4 r = curand4(&st);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    const int64_t base = g * 128;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+#pragma unroll 8
+        for (int i = 0; i < 32; i += 4) {
+            const int64_t o = base + 32 * k + i;
+            const float4 v = make_float4(float((w[k] >> i) & 1u), float((w[k] >> (i + 1)) & 1u), float((w[k] >> (i + 2)) & 1u),
+                                         float((w[k] >> (i + 3)) & 1u));
+            if (o + 3 < n) {
+                *reinterpret_cast<float4 *>(bits + o) = v;
+            } else {
+                if (o < n) bits[o] = v.x;
+                if (o + 1 < n) bits[o + 1] = v.y;
+                if (o + 2 < n) bits[o + 2] = v.z;
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // f3.  Traceback.  survivors[b][t][W] are the bit-packed decisions exported by mvn_acs_decode (bit j of the
 // word group = predecessor choice of new state j < S/2; states j and j+S/2 share it).  State at time t is
@@ -115,6 +143,20 @@ extern "C" int mvn_channel_transmit(const float *bits, int64_t B, int T, int L, 
     const int64_t n = B * T;
     channel_kernel<<<unsigned((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(bits, B, T, L, taps, n_h, sigma, noise,
                                                                                              seed, y);
+    note_launch();
+    MVN_CUDA(cudaGetLastError());
+    return MVN_OK;
+}
+
+extern "C" int mvn_random_bits(float *bits, int64_t B, int T, uint64_t seed, void *stream) {
+    if (B < 0 || T < 1 || (B > 0 && !bits) || (reinterpret_cast<uintptr_t>(bits) & 15u)) {
+        set_error("mvn_random_bits: bad argument (bits must be 16-byte aligned)");
+        return MVN_ERR_ARG;
+    }
+    const int64_t n = B * T;
+    if (n == 0) return MVN_OK;
+    const int64_t groups = (n + 127) / 128;
+    random_bits_kernel<<<unsigned((groups + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(bits, n, seed);
     note_launch();
     MVN_CUDA(cudaGetLastError());
     return MVN_OK;

@@ -16,6 +16,7 @@
 #include <algorithm>
 
 #include "mvn_common.cuh"
+#include "train_gemm.cuh"
 #include "../../include/mvn_b200_train.h"
 
 namespace mvn {
@@ -225,45 +226,6 @@ __device__ __forceinline__ float param_grad(int idx, const float *__restrict__ s
     return acc;
 }
 
-// block-wide sum of per-thread losses (deterministic tree)
-__device__ __forceinline__ float block_sum(float v, float *red) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    float t = 0.f;
-    for (int i = 0; i < kTrainThreads / 32; i++) t += red[i];
-    return t;
-}
-
-// gradient of the mean CE over n symbols at theta `th` -> g (shared or global), returns the loss.
-// Handles n > blockDim by processing symbol blocks of kTrainThreads and accumulating.
-template <int S, bool TAN>
-__device__ float loss_grad(const float *th, const float *tv, const float *__restrict__ y, const int *__restrict__ lab,
-                           int n, float *slab, float *red, float *g_out, bool accumulate_neg_scaled, float scale) {
-    using TV = ThetaView<S>;
-    float loss = 0.f;
-    const float inv_n = 1.f / float(n);
-    for (int base = 0; base < n; base += kTrainThreads) {
-        const int cnt = min(kTrainThreads, n - base);
-        if (int(threadIdx.x) < cnt) {
-            const int i = base + threadIdx.x;
-            loss += symbol_pass<S, TAN>(th, tv, y[i], lab[i], nullptr, inv_n, slab + size_t(threadIdx.x) * Slab<S>::kRow);
-        }
-        __syncthreads();
-        for (int idx = threadIdx.x; idx < TV::P; idx += kTrainThreads) {
-            const float v = param_grad<S, TAN>(idx, slab, y + base, cnt);
-            if (accumulate_neg_scaled)
-                g_out[idx] = (base == 0 ? g_out[idx] : g_out[idx]) + scale * v;  // g_out += scale * v
-            else
-                g_out[idx] = (base == 0 ? 0.f : g_out[idx]) + v;
-        }
-        __syncthreads();
-    }
-    return block_sum(loss, red) * inv_n;
-}
-
 struct AdamCfg {
     float lr, beta1, beta2, eps;
 };
@@ -277,6 +239,24 @@ __device__ __forceinline__ void adam_update(float *theta, float *m, float *v, co
     const float step_size = c.lr / bc1;
     for (int i = threadIdx.x; i < P; i += kTrainThreads) {
         const float gi = g[i];
+        const float mi = m[i] + (1.f - c.beta1) * (gi - m[i]);
+        const float vi = c.beta2 * v[i] + (1.f - c.beta2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + c.eps;
+        theta[i] = theta[i] - step_size * (mi / denom);
+    }
+}
+
+// same update with the gradient read from the padded shared-memory layout
+template <int S>
+__device__ __forceinline__ void adam_update_padded(float *theta, float *m, float *v, const float *g, int step, AdamCfg c) {
+    using LY = tg::Lay<S>;
+    const float bc1 = float(1.0 - pow(double(c.beta1), double(step)));
+    const float bc2_sqrt = float(sqrt(1.0 - pow(double(c.beta2), double(step))));
+    const float step_size = c.lr / bc1;
+    for (int i = threadIdx.x; i < LY::TP; i += tg::kThreads) {
+        const float gi = g[LY::to_padded(i)];
         const float mi = m[i] + (1.f - c.beta1) * (gi - m[i]);
         const float vi = c.beta2 * v[i] + (1.f - c.beta2) * gi * gi;
         m[i] = mi;
@@ -304,53 +284,119 @@ struct TrainParams {
     int update;  // 0: only loss/grad
 };
 
-// shared memory: theta | theta' (fast weights) | g (query gradient / tangent) | red[8]
+// ---------------------------------------------------------------------------------------------
+// Batched step kernels (mvn_train_step_batched / mvn_meta_step_batched): one CTA per realisation, the GEMM-structured
+// passes of train_gemm.cuh.  Shared memory: Wset | Vset (second-order MAML only) | G | activations | red.
+// ---------------------------------------------------------------------------------------------
+constexpr int kCapWide = 136, kLdnWide = 140;   // one word of the reference's coded block per chunk (non-tangent passes)
+constexpr int kCapTan = 72, kLdnTan = 76;       // tangent passes hold two activation sets: half-word chunks
+
 template <int S, bool META>
-__global__ void __launch_bounds__(kTrainThreads, 1) train_step_kernel(TrainParams p) {
-    using TV = ThetaView<S>;
-    constexpr int P = TV::P;
-    constexpr int PP = (P + 3) / 4 * 4;
+struct StepSmem {
+    using LY = tg::Lay<S>;
+    // META: the wide layout for the support / query gradient passes and the two-set narrow layout for the tangent pass
+    // share one region; plain steps use the narrow layout (two CTAs per SM)
+    static constexpr size_t act_floats = META ? (tg::Acts<S>::floats(kLdnWide, false) > tg::Acts<S>::floats(kLdnTan, true)
+                                                     ? tg::Acts<S>::floats(kLdnWide, false)
+                                                     : tg::Acts<S>::floats(kLdnTan, true))
+                                              : tg::Acts<S>::floats(kLdnTan, false);
+    static constexpr size_t floats = size_t(META ? 3 : 2) * LY::PP + act_floats + 32;
+    static constexpr size_t bytes = floats * sizeof(float);
+};
+
+template <int S>
+__device__ __forceinline__ tg::Smem<S> carve(float *sm, bool with_v, bool tangent, int ldn) {
+    using LY = tg::Lay<S>;
+    tg::Smem<S> v;
+    v.W = sm;
+    v.V = with_v ? sm + LY::PP : sm;
+    v.G = sm + (with_v ? 2 : 1) * LY::PP;
+    float *a = v.G + LY::PP;
+    v.red = a;
+    a += 32;
+    v.ldn = ldn;
+    v.y = a;
+    v.H1T = v.y + ldn;
+    v.H2T = v.H1T + kH1 * ldn;
+    v.ZT = v.H2T + tg::kH2P * ldn;
+    v.RH1T = v.ZT + LY::SP * ldn;
+    v.RH2T = v.RH1T + kH1 * ldn;
+    v.RZT = v.RH2T + tg::kH2P * ldn;
+    (void)tangent;
+    return v;
+}
+
+// theta (torch packing, HBM) -> padded layout in shared memory (padding zeroed)
+template <int S>
+__device__ __forceinline__ void load_theta(float *dst, const float *__restrict__ theta) {
+    using LY = tg::Lay<S>;
+    for (int i = threadIdx.x; i < LY::PP; i += tg::kThreads) dst[i] = 0.f;
+    __syncthreads();
+    for (int i = threadIdx.x; i < LY::TP; i += tg::kThreads) dst[LY::to_padded(i)] = theta[i];
+    __syncthreads();
+}
+
+__device__ __forceinline__ float block_sum256(float v, float *red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+    for (int i = 0; i < tg::kWarps; i++) t += red[i];
+    __syncthreads();
+    return t;
+}
+
+template <int S, bool META>
+__global__ void __launch_bounds__(tg::kThreads, META ? 1 : 2) train_step_kernel(TrainParams p) {
+    using LY = tg::Lay<S>;
     extern __shared__ __align__(16) float sm[];
-    float *th = sm, *thf = sm + PP, *g = sm + 2 * PP, *red = sm + 3 * PP;
-    float *slab = p.workspace + size_t(blockIdx.x) * kTrainThreads * Slab<S>::kRow;
+    const int tid = threadIdx.x;
     for (int r = blockIdx.x; r < p.R; r += gridDim.x) {
-        float *theta = p.theta + size_t(r) * P;
-        for (int i = threadIdx.x; i < P; i += kTrainThreads) th[i] = theta[i];
-        __syncthreads();
+        float *theta = p.theta + size_t(r) * LY::TP;
         float loss;
+        tg::Smem<S> v = carve<S>(sm, META, false, META ? kLdnWide : kLdnTan);
+        load_theta<S>(v.W, theta);
+        for (int i = tid; i < LY::PP; i += tg::kThreads) v.G[i] = 0.f;
+        __syncthreads();
         if constexpr (!META) {
-            loss = loss_grad<S, false>(th, th, p.y_s + size_t(r) * p.Ns, p.lab_s + size_t(r) * p.Ns, p.Ns, slab, red, g,
-                                       false, 0.f);
+            loss = block_sum256(tg::pass<S, false>(v, p.y_s + size_t(r) * p.Ns, p.lab_s + size_t(r) * p.Ns, p.Ns,
+                                                   1.f / float(p.Ns), 1.f, kCapTan), v.red) / float(p.Ns);
         } else {
             const float *ys = p.y_s + size_t(r) * p.Ns, *yq = p.y_q + size_t(r) * p.Nq;
             const int *ls = p.lab_s + size_t(r) * p.Ns, *lq = p.lab_q + size_t(r) * p.Nq;
             // inner step on the support set: theta' = theta - meta_lr * grad L_s(theta)   (trainer.py:433-439)
-            loss_grad<S, false>(th, th, ys, ls, p.Ns, slab, red, g, false, 0.f);
-            __syncthreads();
-            for (int i = threadIdx.x; i < P; i += kTrainThreads) thf[i] = th[i] - p.meta_lr * g[i];
+            tg::pass<S, false>(v, ys, ls, p.Ns, 1.f / float(p.Ns), 1.f, kCapWide);
+            for (int i = tid; i < LY::PP; i += tg::kThreads) {
+                v.W[i] -= p.meta_lr * v.G[i];
+                v.G[i] = 0.f;
+            }
             __syncthreads();
             // query loss and its gradient at theta'                                   (trainer.py:442-444)
-            loss = loss_grad<S, false>(thf, thf, yq, lq, p.Nq, slab, red, g, false, 0.f);
-            __syncthreads();
+            loss = block_sum256(tg::pass<S, false>(v, yq, lq, p.Nq, 1.f / float(p.Nq), 1.f, kCapWide), v.red) / float(p.Nq);
             if (p.second_order) {
-                // d/dtheta L_q(theta - a grad L_s(theta)) = g_q - a H_s(theta) g_q: forward-over-reverse
-                // pass of the support loss at theta along g_q, accumulated into thf (free by now).
-                for (int i = threadIdx.x; i < P; i += kTrainThreads) thf[i] = g[i];
-                __syncthreads();
-                loss_grad<S, true>(th, g, ys, ls, p.Ns, slab, red, thf, true, -p.meta_lr);
-                __syncthreads();
-                for (int i = threadIdx.x; i < P; i += kTrainThreads) g[i] = thf[i];
+                // d/dtheta L_q(theta - a grad L_s(theta)) = g_q - a H_s(theta) g_q: forward-over-reverse pass of the
+                // support loss at theta along v = g_q, accumulated into G with scale -a
+                tg::Smem<S> t = carve<S>(sm, true, true, kLdnTan);
+                for (int i = tid; i < LY::PP; i += tg::kThreads) t.V[i] = t.G[i];
+                load_theta<S>(t.W, theta);
+                tg::pass<S, true>(t, ys, ls, p.Ns, 1.f / float(p.Ns), -p.meta_lr, kCapTan);
             }
         }
         __syncthreads();
+        const float *g = v.G;
         if (p.grad_out)
-            for (int i = threadIdx.x; i < P; i += kTrainThreads) p.grad_out[size_t(r) * P + i] = g[i];
-        if (p.loss_out && threadIdx.x == 0) p.loss_out[r] = loss;
-        if (p.update) {
+            for (int i = tid; i < LY::TP; i += tg::kThreads) p.grad_out[size_t(r) * LY::TP + i] = g[LY::to_padded(i)];
+        if (p.loss_out && tid == 0) p.loss_out[r] = loss;
+        // run_train_loop returns before backward / optimizer.step when the loss is NaN (trainer.py:495-498); the
+        // meta loop has no such test (trainer.py:425-453)
+        const bool skip = !META && isnan(loss);
+        if (p.update && !skip) {
             const int step = p.adam_step[r] + 1;
-            adam_update(theta, p.adam_m + size_t(r) * P, p.adam_v + size_t(r) * P, g, P, step, p.adam);
+            adam_update_padded<S>(theta, p.adam_m + size_t(r) * LY::TP, p.adam_v + size_t(r) * LY::TP, g, step, p.adam);
             __syncthreads();
-            if (threadIdx.x == 0) p.adam_step[r] = step;
+            if (tid == 0) p.adam_step[r] = step;
         }
         __syncthreads();
     }
@@ -520,24 +566,19 @@ static int launch_detect_batched(const float *theta, int R, const float *y, int 
 
 static int train_grid(int R) { return std::max(1, std::min(R, 2 * sm_count())); }
 
-template <int S>
-static size_t train_smem() {
-    return (size_t(3) * ((ThetaView<S>::P + 3) / 4 * 4) + 16) * sizeof(float);
-}
-
 template <int L>
 static int launch_train(const TrainParams &p, bool meta, cudaStream_t st) {
     constexpr int S = 1 << L;
-    const size_t smem = train_smem<S>();
-    const int grid = train_grid(p.R);
     if (meta) {
         auto kern = train_step_kernel<S, true>;
+        const size_t smem = StepSmem<S, true>::bytes;
         MVN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        kern<<<grid, kTrainThreads, smem, st>>>(p);
+        kern<<<std::max(1, std::min(p.R, sm_count())), tg::kThreads, smem, st>>>(p);
     } else {
         auto kern = train_step_kernel<S, false>;
+        const size_t smem = StepSmem<S, false>::bytes;
         MVN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        kern<<<grid, kTrainThreads, smem, st>>>(p);
+        kern<<<train_grid(p.R), tg::kThreads, smem, st>>>(p);
     }
     note_launch();
     MVN_CUDA(cudaGetLastError());
@@ -606,10 +647,9 @@ using namespace mvn;
 extern "C" int mvn_param_count(int L) { return (L < 1 || L > 8) ? -1 : param_count_s(1 << L); }
 
 extern "C" int64_t mvn_meta_workspace_bytes(int L, int R, int n_max) {
-    (void)n_max;  // symbols are processed in blocks of 256 per CTA, the slab does not grow with n
-    const size_t row = slab_row_floats(L);
-    if (!row || R < 1) return -1;
-    return int64_t(train_grid(R)) * kTrainThreads * row * sizeof(float);
+    (void)n_max;  // the batched step kernels keep everything in shared memory; the argument survives for ABI stability
+    if (!slab_row_floats(L) || R < 1) return -1;
+    return 256;
 }
 
 extern "C" int64_t mvn_priors_backward_workspace_bytes(int L, int64_t N) {
@@ -620,7 +660,7 @@ extern "C" int64_t mvn_priors_backward_workspace_bytes(int L, int64_t N) {
 }
 
 static int train_common(TrainParams &p, int L, bool meta, void *stream) {
-    if (!p.theta || p.R < 0 || !p.y_s || !p.lab_s || p.Ns < 1 || !p.workspace ||
+    if (!p.theta || p.R < 0 || !p.y_s || !p.lab_s || p.Ns < 1 ||
         (p.update && (!p.adam_m || !p.adam_v || !p.adam_step)) || (meta && (!p.y_q || !p.lab_q || p.Nq < 1))) {
         set_error("batched training step: bad argument");
         return MVN_ERR_ARG;

@@ -86,6 +86,8 @@ struct VnetParams {
     unsigned long long *counters;
     int64_t n_warp_tiles;  // tiles of 32*M frames
     int const_slot;
+    int variant;           // MVN_VARIANT_*: which implementation runs (per call, no global state)
+    int decision;          // MVN_DECIDE_*
 };
 
 // Variant = (frames per lane, weight source, threads per CTA, layer-2 unroll).  One CTA per SM.
@@ -245,8 +247,6 @@ __global__ void __launch_bounds__(V::NT, 1) vnet_decode_kernel(VnetParams p) {
 #include "vnet_tc_kernel.cuh"
 namespace mvn {
 
-static int g_variant = 0;       // tuning knob for memory_length 4 (mvn_debug_set_variant)
-
 // The two constant-bank slots are the only state shared between calls.  Each slot carries an event
 // recorded after the kernel that read it; the next call that wants the slot makes its stream wait
 // on that event before overwriting it, so calls on different streams (and host threads) stay safe.
@@ -297,23 +297,30 @@ static int launch_variant(VnetParams p, cudaStream_t st) {
     return MVN_OK;
 }
 
-// Pipeline-timeout flag of the tcgen05 kernel, in mapped pinned host memory: the kernel raises it if one of its
-// mbarrier waits gives up (never expected: it would mean a protocol bug), the host sees it without a synchronisation and
-// refuses further launches loudly instead of returning words decoded from a broken pipeline.
-static int *g_tc_timeout_host = nullptr, *g_tc_timeout_dev = nullptr;
-static std::once_flag g_tc_timeout_once;
-static int *tc_timeout_flag() {
-    std::call_once(g_tc_timeout_once, [] {
-        if (cudaHostAlloc(reinterpret_cast<void **>(&g_tc_timeout_host), sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) !=
-            cudaSuccess) {
-            g_tc_timeout_host = nullptr;
+// Pipeline watchdog of the tcgen05 kernel (tc::TcWatch): one __device__ flag per GPU that the kernel's waits poll, and one
+// word per GPU in mapped pinned host memory that the kernel writes once if a wait gives up.  The host reads that word
+// without a synchronisation: before a launch (a set flag refuses the launch loudly until mvn_reset_tc_timeout()) and, in
+// the host-buffer entry points, after their own stream syncs — so a call that timed out does not return MVN_OK.
+__device__ int g_tc_watch_dev = 0;
+static int *g_tc_watch_host = nullptr, *g_tc_watch_host_dev = nullptr;   // [64] words, one per device ordinal
+static std::once_flag g_tc_watch_once;
+static bool tc_watch_init() {
+    std::call_once(g_tc_watch_once, [] {
+        if (cudaHostAlloc(reinterpret_cast<void **>(&g_tc_watch_host), 64 * sizeof(int),
+                          cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+            g_tc_watch_host = nullptr;
             return;
         }
-        *g_tc_timeout_host = 0;
-        if (cudaHostGetDevicePointer(reinterpret_cast<void **>(&g_tc_timeout_dev), g_tc_timeout_host, 0) != cudaSuccess)
-            g_tc_timeout_dev = nullptr;
+        for (int i = 0; i < 64; i++) g_tc_watch_host[i] = 0;
+        if (cudaHostGetDevicePointer(reinterpret_cast<void **>(&g_tc_watch_host_dev), g_tc_watch_host, 0) != cudaSuccess)
+            g_tc_watch_host_dev = nullptr;
     });
-    return g_tc_timeout_dev;
+    return g_tc_watch_host && g_tc_watch_host_dev;
+}
+int tc_timeout_seen() {
+    int dev = 0;
+    if (!g_tc_watch_host || cudaGetDevice(&dev) != cudaSuccess) return 0;
+    return g_tc_watch_host[dev & 63];
 }
 #ifdef MVN_TC_TRACE
 __device__ long long g_tc_trace[64 * 32];
@@ -328,15 +335,19 @@ static int launch_tc(VnetParams p, cudaStream_t st) {
     p.n_warp_tiles = (p.B + 31) / 32;
     const int64_t need = (p.n_warp_tiles + 3) / 4;
     const int grid = int(std::min<int64_t>(need, sm_count()));
-    int *flag = tc_timeout_flag();
-    if (!flag) {
-        set_error("vnet_decode (tcgen05): cannot allocate the mapped pipeline-timeout flag");
+    int dev = 0;
+    MVN_CUDA(cudaGetDevice(&dev));
+    if (!tc_watch_init()) {
+        set_error("vnet_decode (tcgen05): cannot allocate the mapped pipeline-watchdog word");
         return MVN_ERR_CUDA;
     }
-    if (*g_tc_timeout_host) {
-        set_error("vnet_decode (tcgen05): a pipeline wait timed out in an earlier launch; results since then are invalid");
+    if (g_tc_watch_host[dev & 63]) {
+        set_error("vnet_decode (tcgen05): a pipeline wait timed out in an earlier launch on this device; its results "
+                  "are invalid.  Call mvn_reset_tc_timeout() to re-arm, or select MVN_VARIANT_FMA");
         return MVN_ERR_CUDA;
     }
+    tc::TcWatch flag{nullptr, g_tc_watch_host_dev + (dev & 63)};
+    MVN_CUDA(cudaGetSymbolAddress(reinterpret_cast<void **>(&flag.dev), g_tc_watch_dev));
     void *trace = nullptr;
 #ifdef MVN_TC_TRACE
     MVN_CUDA(cudaGetSymbolAddress(&trace, g_tc_trace));
@@ -359,12 +370,12 @@ static int launch_tc(VnetParams p, cudaStream_t st) {
 //   L = 8 : as above with one frame per lane (the path metrics take 131 KB of shared memory)
 template <int L>
 static int launch_fused(const VnetParams &p, cudaStream_t st) {
-    const bool want_fma = g_variant == 1 || g_variant == 2 || g_variant == 4;
+    const bool want_fma = p.variant == MVN_VARIANT_FMA_SMEM || p.variant == MVN_VARIANT_FMA_CONST320 || p.variant == MVN_VARIANT_FMA;
     if constexpr (L <= 6) {
-        if (!want_fma) return launch_tc<L>(p, st);  // 0 (auto) and 3
+        if (!want_fma) return launch_tc<L>(p, st);  // auto and tcgen05
     }
     if constexpr (L <= 4) {
-        switch (g_variant) {
+        switch (p.variant) {
             case 1: return launch_variant<L, FusedVariant<L, 2, kSmem, 256, 10>>(p, st);
             case 2: return launch_variant<L, FusedVariant<L, 2, kConst, 320, 10>>(p, st);
             default: return launch_variant<L, FusedVariant<L, 2, kConst, (L <= 3 ? 448 : 384), 10>>(p, st);
@@ -379,8 +390,8 @@ static int launch_fused(const VnetParams &p, cudaStream_t st) {
 }
 
 // frames decoded by one full wave of CTAs (host pipeline chunk sizing)
-int vnet_frames_per_wave(int L) {
-    const int per_cta = (L <= 6 && !(g_variant == 1 || g_variant == 2 || g_variant == 4)) ? 128
+int vnet_frames_per_wave(int L, int variant) {
+    const int per_cta = (L <= 6 && !(variant == 1 || variant == 2 || variant == 4)) ? 128
                         : L <= 3 ? 448 * 2 : L <= 5 ? 384 * 2 : L <= 7 ? 128 * 2 : 128;
     return per_cta * sm_count();
 }
@@ -445,10 +456,10 @@ extern "C" int mvn_vnet_priors(const float *y, int64_t N, int L, const float *w1
     return vnet_priors_impl(y, N, L, w, priors, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int mvn_vnet_decode(const float *y, int64_t B, int T, int L, int n_stages, const float *w1,
-                               const float *b1, const float *w2, const float *b2, const float *w3, const float *b3,
-                               int out_format, void *decoded, float *priors_out, const float *target, int target_T,
-                               int pilot_period, uint64_t *counters, void *stream) {
+extern "C" int mvn_vnet_decode_ex(const float *y, int64_t B, int T, int L, int n_stages, const float *w1,
+                                  const float *b1, const float *w2, const float *b2, const float *w3, const float *b3,
+                                  int out_format, void *decoded, float *priors_out, const float *target, int target_T,
+                                  int pilot_period, uint64_t *counters, int variant, int decision, void *stream) {
     if (L < 1 || L > 8) {
         set_error("memory_length %d outside [1,8]", L);
         return MVN_ERR_ARG;
@@ -458,24 +469,43 @@ extern "C" int mvn_vnet_decode(const float *y, int64_t B, int T, int L, int n_st
         set_error("mvn_vnet_decode: bad argument (B=%lld T=%d n_stages=%d)", (long long)B, T, n_stages);
         return MVN_ERR_ARG;
     }
+    if (variant < MVN_VARIANT_AUTO || variant > MVN_VARIANT_FMA) {
+        set_error("mvn_vnet_decode: unknown kernel variant %d", variant);
+        return MVN_ERR_ARG;
+    }
+    if (decision != MVN_DECIDE_REFERENCE) {
+        set_error("mvn_vnet_decode: decision mode %d not available", decision);
+        return MVN_ERR_UNSUPPORTED;
+    }
     if (target && (!counters || target_T < 1 || target_T > T)) {
         set_error("mvn_vnet_decode: target needs counters and 1 <= target_T <= T");
         return MVN_ERR_ARG;
     }
     if (B == 0 || T == 0) return MVN_OK;
     VnetParams p{y, B, T, n_stages, VnetWeights{w1, b1, w2, b2, w3, b3}, out_format, decoded, priors_out, target,
-                 target_T, pilot_period, reinterpret_cast<unsigned long long *>(counters), 0, 0};
+                 target_T, pilot_period, reinterpret_cast<unsigned long long *>(counters), 0, 0, variant, decision};
     return vnet_decode_impl(p, L, static_cast<cudaStream_t>(stream));
 }
 
-// Tuning knob (not part of the public header): selects the fused-kernel variant for memory_length 4.
-extern "C" int mvn_debug_set_variant(int v) {
-    const int old = g_variant;
-    g_variant = v;
-    return old;
+extern "C" int mvn_vnet_decode(const float *y, int64_t B, int T, int L, int n_stages, const float *w1,
+                               const float *b1, const float *w2, const float *b2, const float *w3, const float *b3,
+                               int out_format, void *decoded, float *priors_out, const float *target, int target_T,
+                               int pilot_period, uint64_t *counters, void *stream) {
+    return mvn_vnet_decode_ex(y, B, T, L, n_stages, w1, b1, w2, b2, w3, b3, out_format, decoded, priors_out, target,
+                              target_T, pilot_period, counters, MVN_VARIANT_AUTO, MVN_DECIDE_REFERENCE, stream);
 }
 
-extern "C" int mvn_debug_tc_timeout(void) { return mvn::g_tc_timeout_host ? *mvn::g_tc_timeout_host : 0; }
+/* 1 if a tcgen05 pipeline wait timed out on the current device since the last reset */
+extern "C" int mvn_tc_timeout_status(void) { return mvn::tc_timeout_seen(); }
+
+extern "C" int mvn_reset_tc_timeout(void) {
+    int dev = 0;
+    MVN_CUDA(cudaGetDevice(&dev));
+    const int zero = 0;
+    MVN_CUDA(cudaMemcpyToSymbol(mvn::g_tc_watch_dev, &zero, sizeof(int)));
+    if (mvn::g_tc_watch_host) mvn::g_tc_watch_host[dev & 63] = 0;
+    return MVN_OK;
+}
 
 #ifdef MVN_TC_TRACE
 extern "C" int mvn_debug_tc_trace(long long *host_out) {

@@ -98,10 +98,25 @@ __device__ __forceinline__ void tmem_ld16(uint32_t addr, float *r) {
 // try_wait with a suspend-time hint: the waiting warp is parked by the hardware until the phase completes (or the
 // hint expires) instead of spinning.  A spinning warp competes for the issue slots of its scheduler; the MMA warp
 // waits most of the time and made the producers that share its scheduler the slowest of the CTA (pipeline trace).
+// Pipeline watchdog: a wait that has not completed after kWaitTimeoutNs of wall clock (%globaltimer) raises the
+// launch's flag — a DEVICE word that every other wait of the grid polls (an L2 hit) so the launch drains quickly —
+// and reports once to the mapped host word the library checks before the next launch and after its own syncs.
+// Never expected (it would mean a protocol bug or a wedged producer); keeps a bug from hanging the GPU.
+struct TcWatch {
+    int *dev;    // __device__ flag of this GPU
+    int *host;   // mapped pinned host word of this GPU
+};
+constexpr unsigned long long kWaitTimeoutNs = 2000000000ull;
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 template <bool PARK = true>
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int *timeout_flag) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, TcWatch watch) {
     uint32_t done = 0;
     int spins = 0;
+    unsigned long long t_start = 0;
     while (!done) {
         if (PARK)
             asm volatile(
@@ -115,12 +130,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int *ti
                 : "=r"(done)
                 : "r"(bar), "r"(parity)
                 : "memory");
-        // never expected; keeps a bug from hanging the GPU: the first wait that gives up raises the flag, and every other
-        // wait of the grid bails out as soon as it sees it (the launch then ends quickly, with the flag set for the host)
-        if (!done && timeout_flag && (++spins & (PARK ? 7 : 1023)) == 0) {
-            if (*reinterpret_cast<volatile int *>(timeout_flag)) break;
-            if (spins > (PARK ? (1 << 12) : (1 << 24))) {
-                *timeout_flag = 1;
+        if (!done && watch.dev && (++spins & (PARK ? 7 : 1023)) == 0) {
+            if (*reinterpret_cast<volatile int *>(watch.dev)) break;
+            const unsigned long long now = globaltimer_ns();
+            if (t_start == 0) t_start = now;
+            if (now - t_start > kWaitTimeoutNs) {
+                *reinterpret_cast<volatile int *>(watch.dev) = 1;
+                if (watch.host) *reinterpret_cast<volatile int *>(watch.host) = 1;
+                __threadfence_system();
                 break;
             }
         }
@@ -265,7 +282,7 @@ __device__ __forceinline__ void h2_to_tmem(uint32_t slot_lane) {
 #endif
 
 template <int L>
-__global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, int *timeout_flag, long long *trace) {
+__global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch timeout_flag, long long *trace) {
     static_assert(L <= 6, "tcgen05 variant: the priors of one stage must fit a 64-column TMEM region");
     using D = TrellisDims<L>;
     constexpr int S = D::S, C = D::C, NCH = D::NCH, NW = tc::kProdWarps + tc::kConvWarps + tc::kConsWarps;

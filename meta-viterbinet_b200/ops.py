@@ -5,19 +5,32 @@ from . import _lib
 from ._lib import OUT_BITS, OUT_F32, check, dev_f32, load, ptr, stream
 
 
-FUSED_VARIANTS = {'auto': 0, 'fma_smem': 1, 'fma_const_320': 2, 'tcgen05': 3, 'fma': 4}
+FUSED_VARIANTS = {'auto': 0, 'fma_smem': 1, 'fma_const_320': 2, 'tcgen05': 3, 'fma': 4}     # MVN_VARIANT_*
+DECISIONS = {'reference': 0, 'mlse': 1, 'mlse_terminated': 2}                               # MVN_DECIDE_*
+_default_variant = 'auto'
 
 
 def set_fused_variant(name: str = 'auto') -> str:
-    """Select the implementation of the fused ViterbiNet kernel for memory_length 4 (tuning / testing):
-    'auto' (library default), 'tcgen05' (layer 2 on the tensor cores, bf16x6 split), 'fma' (FP32 FMA pipe,
-    constant-bank weights), 'fma_smem'.  Returns the previous selection."""
-    import ctypes
-    lib = load()
-    lib.mvn_debug_set_variant.restype = ctypes.c_int
-    lib.mvn_debug_set_variant.argtypes = [ctypes.c_int]
-    old = lib.mvn_debug_set_variant(FUSED_VARIANTS[name])
-    return {v: k for k, v in FUSED_VARIANTS.items()}.get(old, 'auto')
+    """Default implementation of the fused ViterbiNet kernel for calls that do not pass `variant` (tuning / testing):
+    'auto' (library default: layers 2-3 on the tcgen05 tensor cores with an fp16 two-piece split, every memory
+    length), 'tcgen05' (the same, explicitly), 'fma' (FP32 FMA pipe, constant-bank weights), 'fma_smem' (FP32 FMA
+    pipe, weights in shared memory), 'fma_const_320'.  This is a Python-side default only: the C library itself keeps
+    no such switch, the variant travels with every call (mvn_vnet_decode_ex).  Returns the previous selection."""
+    global _default_variant
+    if name not in FUSED_VARIANTS:
+        raise ValueError(f'unknown fused-kernel variant {name!r}')
+    old, _default_variant = _default_variant, name
+    return old
+
+
+def tc_timeout_status() -> bool:
+    """True if the tensor-core kernel's pipeline watchdog fired on the current device since the last reset (check it
+    after synchronising when the output of an asynchronous vnet_decode matters)."""
+    return bool(load().mvn_tc_timeout_status())
+
+
+def reset_tc_timeout():
+    check(load().mvn_reset_tc_timeout())
 
 
 def _mem_len(n_states: int) -> int:
@@ -74,8 +87,9 @@ def acs_decode(cost, n_stages=None, out_format=OUT_F32, return_final_pm=False, r
 
 
 def va_decode(y, state_priors, n_stages=None, out_format=OUT_F32, target=None, pilot_period=0, counters=None,
-              want_decoded=True):
-    """Fused full-CSI Viterbi.  state_priors [n_h, S] fp32 (row per tap block)."""
+              want_decoded=True, decision='reference'):
+    """Fused full-CSI Viterbi.  state_priors [n_h, S] fp32 (row per tap block).  decision: 'reference' (the reference's
+    running-argmin rule), 'mlse' / 'mlse_terminated' (in-kernel survivor traceback)."""
     y = dev_f32(y)
     sp = dev_f32(state_priors)
     B, T = y.shape
@@ -89,8 +103,8 @@ def va_decode(y, state_priors, n_stages=None, out_format=OUT_F32, target=None, p
         tT = tgt.shape[1]
         if counters is None:
             raise ValueError('target given without counters')
-    check(load().mvn_va_decode(ptr(y), B, T, L, n, ptr(sp), n_h, out_format, ptr(dec), ptr(tgt), tT, pilot_period,
-                               ptr(counters), stream()))
+    check(load().mvn_va_decode_ex(ptr(y), B, T, L, n, ptr(sp), n_h, out_format, ptr(dec), ptr(tgt), tT, pilot_period,
+                                  ptr(counters), DECISIONS[decision], stream()))
     return dec
 
 
@@ -117,8 +131,9 @@ def vnet_priors(y, weights):
 
 
 def vnet_decode(y, weights, n_stages=None, out_format=OUT_F32, return_priors=False, target=None, pilot_period=0,
-                counters=None, want_decoded=True):
-    """Fused priors MLP + stage loop + decision."""
+                counters=None, want_decoded=True, variant=None, decision='reference'):
+    """Fused priors MLP + stage loop + decision.  variant: one of FUSED_VARIANTS (None = set_fused_variant's default);
+    decision as in va_decode."""
     y = dev_f32(y)
     ws, S = _weights(weights)
     L = _mem_len(S)
@@ -132,8 +147,9 @@ def vnet_decode(y, weights, n_stages=None, out_format=OUT_F32, return_priors=Fal
         tT = tgt.shape[1]
         if counters is None:
             raise ValueError('target given without counters')
-    check(load().mvn_vnet_decode(ptr(y), B, T, L, n, *[ptr(w) for w in ws], out_format, ptr(dec), ptr(pri), ptr(tgt),
-                                 tT, pilot_period, ptr(counters), stream()))
+    check(load().mvn_vnet_decode_ex(ptr(y), B, T, L, n, *[ptr(w) for w in ws], out_format, ptr(dec), ptr(pri), ptr(tgt),
+                                    tT, pilot_period, ptr(counters), FUSED_VARIANTS[variant or _default_variant],
+                                    DECISIONS[decision], stream()))
     return (dec, pri) if return_priors else dec
 
 
@@ -240,12 +256,13 @@ def mlse_decode(cost, n_stages=None, terminated=False, out_format=OUT_F32):
 
 
 def va_mlse_decode(y, state_priors, n_stages=None, terminated=True, out_format=OUT_F32):
-    """Full-CSI Viterbi with traceback: branch metrics as in va_decode, decisions by MLSE."""
-    lib = _bind_next()
-    y = dev_f32(y)
-    sp = dev_f32(state_priors)
-    B, T = y.shape
-    n_h, S = sp.shape
-    cost = torch.empty((B, T, S), dtype=torch.float32, device=y.device)
-    check(lib.mvn_va_cost(ptr(y), B, T, _mem_len(S), ptr(sp), n_h, ptr(cost), stream()))
-    return mlse_decode(cost, n_stages, terminated, out_format)
+    """Full-CSI Viterbi with traceback: branch metrics as in va_decode, decisions by true MLSE.  One fused launch:
+    the survivor bits live in shared memory and the traceback runs in the kernel (mvn_va_decode_ex)."""
+    return va_decode(y, state_priors, n_stages, out_format, decision='mlse_terminated' if terminated else 'mlse')
+
+
+def random_bits(B, T, seed=0, device=None):
+    """Bernoulli(1/2) words [B,T] fp32 on the device (Philox; the role of word_rand_gen.randint, channel_dataset.py:67)."""
+    out = torch.empty((B, T), dtype=torch.float32, device=device or _lib.require_cuda())
+    check(load().mvn_random_bits(ptr(out), B, T, int(seed), stream()))
+    return out

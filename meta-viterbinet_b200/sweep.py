@@ -20,10 +20,14 @@ def partition(n_items: int, world_size: int, rank: int) -> range:
 
 
 def work_items(n_points: int, world_size: int) -> List[Tuple[int, int, int]]:
-    """(point index, block index, blocks per point).  Whole points per rank when there are enough of
-    them (weights differ per SNR point, trainer.py:511); otherwise every point's frames are split into
-    ceil(world/n_points) row blocks so that all ranks have work."""
-    blocks = 1 if n_points >= world_size else -(-world_size // n_points)
+    """(point index, block index, blocks per point), ordered so that partition() hands every rank the same number of
+    items.  Whole points per rank when they divide evenly over the ranks (weights differ per SNR point,
+    trainer.py:511, so a rank then stages each point's weights once); otherwise every point's frames are split into
+    world / gcd(points, world) row blocks: points * blocks is the least common multiple of points and world, i.e. the
+    coarsest split in which all ranks get exactly the same share (6 points on 8 ranks: 4 blocks per point, 3 items
+    per rank — not 2 blocks, which would leave half the ranks with one item and the others with two)."""
+    import math
+    blocks = 1 if n_points % world_size == 0 else world_size // math.gcd(n_points, world_size)
     return [(i, b, blocks) for i in range(n_points) for b in range(blocks)]
 
 

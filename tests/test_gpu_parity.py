@@ -320,7 +320,7 @@ def test_vnet_fused_edge_shapes_with_counters(mvn, fused_impl, L):
         ref = orc.vnet_decode_from_priors(pri, n)[0] if n > 0 else np.zeros_like(dec)
         assert np.array_equal(dec, ref), (L, B, T, n)
         assert cnt.cpu().tolist() == [int((dec != tgt).sum()), int((dec != tgt).any(axis=1).sum()), B * T, B]
-    f = mvn._lib.load().mvn_debug_tc_timeout
+    f = mvn._lib.load().mvn_tc_timeout_status
     f.restype = ctypes.c_int
     assert f() == 0
 
@@ -610,6 +610,54 @@ def test_mlse_traceback_vs_oracle(mvn, L):
         assert np.array_equal(dec.cpu().numpy(), ref)
     words = mvn.ops.mlse_decode(cu(cost), out_format=mvn.OUT_BITS)
     assert np.array_equal(mvn.ops.unpack_bits(words, T).cpu().numpy(), orc.mlse_decode(cost)[0])
+
+
+@pytest.mark.parametrize('L', range(1, 9))
+def test_va_fused_mlse_vs_oracle(mvn, L):
+    """decision = MLSE inside mvn_va_decode_ex (survivor masks in shared memory, in-kernel traceback): same bits as the
+    oracle's traceback over the reference's acs_block survivors (trellis_utils.py:30), both start rules, loops that end
+    mid-tile, bit-packed output, fused counters."""
+    from meta_viterbinet_b200.channel_taps import state_priors_table
+    rng = np.random.RandomState(50 + L)
+    B, T = 77, 70
+    h = (np.exp(-0.3 * np.arange(L)) * (1 + 0.1 * rng.randn(7, L))).astype(np.float64)     # 7 tap blocks, B % 7 == 0
+    bits = rng.randint(0, 2, size=(B, T))
+    y = orc.isi_awgn(bits, h[np.arange(B) % 7], 6.0, L, rng).astype(np.float32)
+    y[:5] = np.round(y[:5])                                                               # coarse values: exact ties
+    table = state_priors_table(h, L)
+    cost = orc.va_cost(y, orc.va_state_priors(h, L))
+    for n_stages, term in ((T, False), (T, True), (T - 9, False), (33, True), (1, False), (0, True)):
+        ref = orc.mlse_decode(cost, n_stages, 0 if term else -1)[0]
+        cnt = mvn.ops.new_counters()
+        tgt = cu(bits.astype(np.float32))
+        dec = mvn.ops.va_decode(cu(y), cu(table), n_stages, decision='mlse_terminated' if term else 'mlse', target=tgt,
+                                pilot_period=5, counters=cnt).cpu().numpy()
+        assert np.array_equal(dec, ref), (L, n_stages, term)
+        keep = np.arange(B) % 5 != 0
+        assert cnt.tolist() == [int((ref[keep] != bits[keep]).sum()), int((ref[keep] != bits[keep]).any(axis=1).sum()),
+                                int(keep.sum()) * T, int(keep.sum())]
+    words = mvn.ops.va_decode(cu(y), cu(table), decision='mlse', out_format=mvn.OUT_BITS)
+    assert np.array_equal(mvn.ops.unpack_bits(words, T).cpu().numpy(), orc.mlse_decode(cost)[0])
+    # per stage, the survivors the traceback walks are the reference's acs_block indices (checked through mvn_acs_decode)
+    _, _, surv = mvn.ops.acs_decode(cu(cost), return_final_pm=True, return_survivors=True)
+    H = max(1, 2 ** L // 2)
+    assert np.array_equal(unpack_survivors(surv, H), orc.acs_decode(cost, return_survivors=True)[2][:, :, :H])
+
+
+def test_va_fused_mlse_full_size(mvn):
+    """2^20 frames x 120: replicas of 4096 oracle-decoded frames in shuffled order decode identically (one launch)"""
+    from meta_viterbinet_b200.channel_taps import state_priors_table
+    rng = np.random.RandomState(8)
+    L, T, U, B = 4, 120, 4096, 1 << 20
+    h = np.exp(-0.2 * np.arange(L)).reshape(1, L)
+    bits = rng.randint(0, 2, size=(U, T))
+    y_u = orc.isi_awgn(bits, h, 8.0, L, rng).astype(np.float32)
+    ref = torch.as_tensor(orc.mlse_decode(orc.va_cost(y_u, orc.va_state_priors(h, L)), start_state=0)[0]).cuda()
+    perm = torch.randint(0, U, (B,), generator=torch.Generator().manual_seed(2)).cuda()
+    n0 = mvn._lib.launch_count(reset=True)
+    dec = mvn.ops.va_mlse_decode(cu(y_u)[perm].contiguous(), cu(state_priors_table(h, L)), terminated=True)
+    assert mvn._lib.launch_count() == 1
+    assert torch.equal(dec, ref[perm])
 
 
 def test_va_mlse_beats_the_reference_rule(mvn):

@@ -63,5 +63,10 @@ def test_partition_and_work_items():
             assert sum(len(p) for p in parts) == n
             assert [i for p in parts for i in p] == list(range(n))
             assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
-    assert sweep.work_items(6, 8) == [(i, b, 2) for i in range(6) for b in range(2)]
-    assert sweep.work_items(6, 4) == [(i, 0, 1) for i in range(6)]
+    assert sweep.work_items(6, 8) == [(i, b, 4) for i in range(6) for b in range(4)]     # 24 items, 3 per rank
+    assert sweep.work_items(6, 4) == [(i, b, 2) for i in range(6) for b in range(2)]     # 12 items, 3 per rank
+    assert sweep.work_items(6, 3) == [(i, 0, 1) for i in range(6)]                       # whole points, 2 per rank
+    for points in range(1, 13):                                   # every rank gets exactly the same number of items
+        for w in (1, 2, 3, 4, 6, 8):
+            items = sweep.work_items(points, w)
+            assert len({len(sweep.partition(len(items), w, r)) for r in range(w)}) == 1, (points, w)

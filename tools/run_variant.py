@@ -16,8 +16,7 @@ dev = torch.device('cuda', 0)
 w = bench.make_weights(torch, dev)
 bits, y = bench.synth_frames(torch, dev, frames, 10, 1)
 lib = _lib.load()
-lib.mvn_debug_set_variant.argtypes = [ctypes.c_int]
-lib.mvn_debug_set_variant(v)
+mvn.ops.set_fused_variant({x: k for k, x in mvn.ops.FUSED_VARIANTS.items()}[v])
 for _ in range(3):
     out = mvn.ops.vnet_decode(y, w)
 torch.cuda.synchronize()

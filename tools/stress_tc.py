@@ -19,5 +19,5 @@ for L in (4, 3, 5, 6, 1):
     for it in range(12):
         out = mvn.ops.vnet_decode(y, w)
         bad += int((out != ref).sum())
-    f = mvn._lib.load().mvn_debug_tc_timeout; f.restype = ctypes.c_int
+    f = mvn._lib.load().mvn_tc_timeout_status; f.restype = ctypes.c_int
     print(f'L={L}: 12 repeats of {frames} frames x {y.shape[1]}: differing symbols vs first run {bad}; frames differing from the FMA kernel {diff_frames} of 65536; timeout flag {f()}', flush=True)

@@ -1,4 +1,4 @@
-"""Times every fused-kernel variant (mvn_debug_set_variant) on the bench workload and checks that all of
+"""Times every fused-kernel variant (ops.set_fused_variant) on the bench workload and checks that all of
 them produce identical bits.  Usage (GPU box): python tools/tune_fused.py [frames]"""
 import ctypes
 import os
@@ -16,12 +16,10 @@ dev = torch.device('cuda', 0)
 w = bench.make_weights(torch, dev)
 bits, y = bench.synth_frames(torch, dev, frames, 10, 1)
 lib = _lib.load()
-lib.mvn_debug_set_variant.restype = ctypes.c_int
-lib.mvn_debug_set_variant.argtypes = [ctypes.c_int]
 names = {4: 'fma const M2 384 u10', 1: 'fma smem M2 256 u10', 2: 'fma const M2 320 u10', 3: 'tcgen05 warp-specialised fp16x2 (default)'}
 ref = None
 for v in (4, 1, 3):
-    lib.mvn_debug_set_variant(v)
+    mvn.ops.set_fused_variant({x: k for k, x in mvn.ops.FUSED_VARIANTS.items()}[v])
     out = mvn.ops.vnet_decode(y, w)
     torch.cuda.synchronize()
     if ref is None:
@@ -43,6 +41,6 @@ for v in (4, 1, 3):
     rate = frames * bench.T / ms / 1e6
     print(f'variant {v} [{names[v]:26s}] {ms:8.3f} ms  {rate:7.3f} Gsym/s  {rate * bench.FLOP_PER_SYMBOL / 1e3:6.2f} TFLOP/s  '
           f'bits_equal_to_fma={same} frames_differing={nbad} priors_rel_vs_fma={rel:.2e}', flush=True)
-lib.mvn_debug_set_variant(0)
-lib.mvn_debug_tc_timeout.restype = ctypes.c_int
-print('tc timeout flag:', lib.mvn_debug_tc_timeout())
+mvn.ops.set_fused_variant({x: k for k, x in mvn.ops.FUSED_VARIANTS.items()}[0])
+lib.mvn_tc_timeout_status.restype = ctypes.c_int
+print('tc timeout flag:', lib.mvn_tc_timeout_status())
