@@ -10,7 +10,8 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_uint
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libmvn_b200.so')
+# MVN_LIB: load another build of the same library (kernel tuning: tools/ compare variants built with -D flags)
+LIB_PATH = os.environ.get('MVN_LIB') or os.path.join(HERE, 'libmvn_b200.so')
 
 OUT_F32 = 0
 OUT_BITS = 1

@@ -248,15 +248,17 @@ __device__ __forceinline__ void adam_update(float *theta, float *m, float *v, co
     }
 }
 
-// same update with the gradient read from the padded shared-memory layout
+// same update with the gradient read from the padded shared-memory layout; bc = (1 - b1^t, sqrt(1 - b2^t)) computed once
+// per CTA in double like torch does on the host
 template <int S>
-__device__ __forceinline__ void adam_update_padded(float *theta, float *m, float *v, const float *g, int step, AdamCfg c) {
+__device__ __forceinline__ void adam_update_padded(float *__restrict__ theta, float *__restrict__ m, float *__restrict__ v,
+                                                   const float *__restrict__ g, const float *__restrict__ bc, AdamCfg c) {
     using LY = tg::Lay<S>;
-    const float bc1 = float(1.0 - pow(double(c.beta1), double(step)));
-    const float bc2_sqrt = float(sqrt(1.0 - pow(double(c.beta2), double(step))));
-    const float step_size = c.lr / bc1;
+    const float step_size = c.lr / bc[0], bc2_sqrt = bc[1];
+#pragma unroll 4
     for (int i = threadIdx.x; i < LY::TP; i += tg::kThreads) {
-        const float gi = g[LY::to_padded(i)];
+        const int ip = i < LY::tb2 ? i : LY::to_padded(i);
+        const float gi = g[ip];
         const float mi = m[i] + (1.f - c.beta1) * (gi - m[i]);
         const float vi = c.beta2 * v[i] + (1.f - c.beta2) * gi * gi;
         m[i] = mi;
@@ -289,23 +291,24 @@ struct TrainParams {
 // passes of train_gemm.cuh.  Shared memory: Wset | Vset (second-order MAML only) | G | activations | red.
 // ---------------------------------------------------------------------------------------------
 constexpr int kCapWide = 136, kLdnWide = 140;   // one word of the reference's coded block per chunk (non-tangent passes)
-constexpr int kCapTan = 72, kLdnTan = 76;       // tangent passes hold two activation sets: half-word chunks
+// tangent passes hold two activation sets: half-word chunks (a third of a word at 32 states, where the sets are larger)
+template <int S> struct TanCap { static constexpr int cap = S <= 16 ? 72 : 56, ldn = cap + 4; };
+constexpr int kCapPlain = 72, kLdnPlain = 76;   // plain steps: narrow layout, two CTAs per SM
 
 template <int S, bool META>
 struct StepSmem {
     using LY = tg::Lay<S>;
     // META: the wide layout for the support / query gradient passes and the two-set narrow layout for the tangent pass
-    // share one region; plain steps use the narrow layout (two CTAs per SM)
-    static constexpr size_t act_floats = META ? (tg::Acts<S>::floats(kLdnWide, false) > tg::Acts<S>::floats(kLdnTan, true)
-                                                     ? tg::Acts<S>::floats(kLdnWide, false)
-                                                     : tg::Acts<S>::floats(kLdnTan, true))
-                                              : tg::Acts<S>::floats(kLdnTan, false);
-    static constexpr size_t floats = size_t(META ? 3 : 2) * LY::PP + act_floats + 32;
+    // share one region
+    static constexpr size_t wide = tg::act_floats<S>(kLdnWide, false), tan = tg::act_floats<S>(TanCap<S>::ldn, true);
+    static constexpr size_t acts = META ? (wide > tan ? wide : tan) : tg::act_floats<S>(kLdnPlain, false) - size_t(tg::kH2P) * kLdnPlain;
+    static constexpr size_t floats = size_t(META ? 3 : 2) * LY::PP + acts + 32;
     static constexpr size_t bytes = floats * sizeof(float);
+    static_assert(bytes <= 227 * 1024, "step kernel: shared memory of one CTA");
 };
 
 template <int S>
-__device__ __forceinline__ tg::Smem<S> carve(float *sm, bool with_v, bool tangent, int ldn) {
+__device__ __forceinline__ tg::Smem<S> carve(float *sm, bool with_v, int ldn, bool separate_da2 = true) {
     using LY = tg::Lay<S>;
     tg::Smem<S> v;
     v.W = sm;
@@ -319,10 +322,11 @@ __device__ __forceinline__ tg::Smem<S> carve(float *sm, bool with_v, bool tangen
     v.H1T = v.y + ldn;
     v.H2T = v.H1T + kH1 * ldn;
     v.ZT = v.H2T + tg::kH2P * ldn;
-    v.RH1T = v.ZT + LY::SP * ldn;
+    v.DA2T = separate_da2 ? v.ZT + LY::SP * ldn : v.H2T;
+    v.RH1T = v.ZT + LY::SP * ldn + (separate_da2 ? tg::kH2P * ldn : 0);
     v.RH2T = v.RH1T + kH1 * ldn;
     v.RZT = v.RH2T + tg::kH2P * ldn;
-    (void)tangent;
+    v.RDA2T = v.RZT + LY::SP * ldn;
     return v;
 }
 
@@ -330,9 +334,16 @@ __device__ __forceinline__ tg::Smem<S> carve(float *sm, bool with_v, bool tangen
 template <int S>
 __device__ __forceinline__ void load_theta(float *dst, const float *__restrict__ theta) {
     using LY = tg::Lay<S>;
-    for (int i = threadIdx.x; i < LY::PP; i += tg::kThreads) dst[i] = 0.f;
-    __syncthreads();
-    for (int i = threadIdx.x; i < LY::TP; i += tg::kThreads) dst[LY::to_padded(i)] = theta[i];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < LY::tb2; i += tg::kThreads) dst[i] = theta[i];                       // w1, b1, W2 rows 0..49
+    for (int i = tid; i < 2 * kH1; i += tg::kThreads) dst[LY::w2 + kH2 * kH1 + i] = 0.f;        // W2 rows 50, 51
+    for (int i = tid; i < tg::kH2P; i += tg::kThreads) dst[LY::b2 + i] = i < kH2 ? theta[LY::tb2 + i] : 0.f;
+    for (int i = tid; i < LY::SP * tg::kH2P; i += tg::kThreads) {
+        const int s = i / tg::kH2P, o = i - s * tg::kH2P;
+        dst[LY::w3 + i] = (s < S && o < kH2) ? theta[LY::tw3 + s * kH2 + o] : 0.f;
+    }
+    for (int i = tid; i < LY::SP; i += tg::kThreads) dst[LY::b3 + i] = i < S ? theta[LY::tb3 + i] : 0.f;
+    for (int i = LY::P + tid; i < LY::PP; i += tg::kThreads) dst[i] = 0.f;
     __syncthreads();
 }
 
@@ -356,32 +367,34 @@ __global__ void __launch_bounds__(tg::kThreads, META ? 1 : 2) train_step_kernel(
     for (int r = blockIdx.x; r < p.R; r += gridDim.x) {
         float *theta = p.theta + size_t(r) * LY::TP;
         float loss;
-        tg::Smem<S> v = carve<S>(sm, META, false, META ? kLdnWide : kLdnTan);
+        tg::Smem<S> v = carve<S>(sm, META, META ? kLdnWide : kLdnPlain, META);
         load_theta<S>(v.W, theta);
         for (int i = tid; i < LY::PP; i += tg::kThreads) v.G[i] = 0.f;
         __syncthreads();
         if constexpr (!META) {
-            loss = block_sum256(tg::pass<S, false>(v, p.y_s + size_t(r) * p.Ns, p.lab_s + size_t(r) * p.Ns, p.Ns,
-                                                   1.f / float(p.Ns), 1.f, kCapTan), v.red) / float(p.Ns);
+            loss = block_sum256(tg::pass<S, false, false>(v, p.y_s + size_t(r) * p.Ns, p.lab_s + size_t(r) * p.Ns, p.Ns,
+                                                   1.f / float(p.Ns), 1.f, kCapPlain), v.red) / float(p.Ns);
         } else {
             const float *ys = p.y_s + size_t(r) * p.Ns, *yq = p.y_q + size_t(r) * p.Nq;
             const int *ls = p.lab_s + size_t(r) * p.Ns, *lq = p.lab_q + size_t(r) * p.Nq;
-            // inner step on the support set: theta' = theta - meta_lr * grad L_s(theta)   (trainer.py:433-439)
-            tg::pass<S, false>(v, ys, ls, p.Ns, 1.f / float(p.Ns), 1.f, kCapWide);
+            // gradient of the support loss at theta, inner step theta' = theta - meta_lr * grad   (trainer.py:433-439),
+            // then the query loss and its gradient at theta'                                    (trainer.py:442-444)
+            float part = 0.f;
+            tg::pass<S, false, true>(v, ys, ls, p.Ns, 1.f / float(p.Ns), 1.f, kCapWide);
             for (int i = tid; i < LY::PP; i += tg::kThreads) {
                 v.W[i] -= p.meta_lr * v.G[i];
                 v.G[i] = 0.f;
             }
             __syncthreads();
-            // query loss and its gradient at theta'                                   (trainer.py:442-444)
-            loss = block_sum256(tg::pass<S, false>(v, yq, lq, p.Nq, 1.f / float(p.Nq), 1.f, kCapWide), v.red) / float(p.Nq);
+            part = tg::pass<S, false, true>(v, yq, lq, p.Nq, 1.f / float(p.Nq), 1.f, kCapWide);
+            loss = block_sum256(part, v.red) / float(p.Nq);
             if (p.second_order) {
                 // d/dtheta L_q(theta - a grad L_s(theta)) = g_q - a H_s(theta) g_q: forward-over-reverse pass of the
                 // support loss at theta along v = g_q, accumulated into G with scale -a
-                tg::Smem<S> t = carve<S>(sm, true, true, kLdnTan);
+                tg::Smem<S> t = carve<S>(sm, true, TanCap<S>::ldn);
                 for (int i = tid; i < LY::PP; i += tg::kThreads) t.V[i] = t.G[i];
                 load_theta<S>(t.W, theta);
-                tg::pass<S, true>(t, ys, ls, p.Ns, 1.f / float(p.Ns), -p.meta_lr, kCapTan);
+                tg::pass<S, true, true>(t, ys, ls, p.Ns, 1.f / float(p.Ns), -p.meta_lr, TanCap<S>::cap);
             }
         }
         __syncthreads();
@@ -394,7 +407,12 @@ __global__ void __launch_bounds__(tg::kThreads, META ? 1 : 2) train_step_kernel(
         const bool skip = !META && isnan(loss);
         if (p.update && !skip) {
             const int step = p.adam_step[r] + 1;
-            adam_update_padded<S>(theta, p.adam_m + size_t(r) * LY::TP, p.adam_v + size_t(r) * LY::TP, g, step, p.adam);
+            if (tid == 0) {
+                v.red[0] = float(1.0 - pow(double(p.adam.beta1), double(step)));
+                v.red[1] = float(sqrt(1.0 - pow(double(p.adam.beta2), double(step))));
+            }
+            __syncthreads();
+            adam_update_padded<S>(theta, p.adam_m + size_t(r) * LY::TP, p.adam_v + size_t(r) * LY::TP, g, v.red, p.adam);
             __syncthreads();
             if (tid == 0) p.adam_step[r] = step;
         }

@@ -163,10 +163,11 @@ def eval_by_word(trainer, info_bits, received, n_symbols, ser_thresh, data_mask=
         detected = trainer.detect(y)                      # self.detector(received_word, 'val', ...) with each run's weights
         if bool(data_mask[c]):
             decoded = ops.rs_decode(detected, n_symbols)
-            ser32 = (decoded != info[:, c]).float().sum(dim=1) / n_info        # calculate_error_rates: fp32 mean
+            # calculate_error_rates (metrics.py:11-17): accuracy = fp32 mean of the equal bits, ser = max(1 - acc, 0) in double
+            acc32 = (decoded == info[:, c]).float().sum(dim=1) / n_info
+            ser = (1.0 - acc32.double()).clamp(min=0.0)
             encoded = ops.rs_encode(decoded, n_symbols)
-            label = torch.where((ser32 > 0).unsqueeze(1), detected, encoded)  # trainer.py:322-324
-            ser = ser32.double()
+            label = torch.where((ser > 0).unsqueeze(1), detected, encoded)    # trainer.py:322-324
             ser_by_word[:, c] = ser
         else:                                             # pilot: the receiver knows the word (trainer.py:310-316)
             label = ops.rs_encode(info[:, c].contiguous(), n_symbols)
