@@ -150,6 +150,13 @@ int mvn_ctx_vnet_decode_host(mvn_ctx *ctx, const float *y_host, int64_t B, int T
                              int out_format, void *decoded_host);
 int mvn_ctx_va_decode_host(mvn_ctx *ctx, const float *y_host, int64_t B, int T, int n_stages,
                            const float *state_priors_host, int n_h, int out_format, void *decoded_host);
+/* Asynchronous form for streaming several batches (e.g. the points of an SNR sweep, each after its own
+ * mvn_ctx_set_vnet_weights_host: the context keeps a ring of 8 weight sets) through ONE pipeline without draining it
+ * between them: returns once everything is enqueued; the host buffers must stay valid, and the results are complete,
+ * after mvn_ctx_synchronize (which also reports CUDA errors and the tcgen05 watchdog of the enqueued work). */
+int mvn_ctx_vnet_decode_host_async(mvn_ctx *ctx, const float *y_host, int64_t B, int T, int n_stages, int out_format,
+                                   void *decoded_host);
+int mvn_ctx_synchronize(mvn_ctx *ctx);
 /* kernel variant (MVN_VARIANT_*) and decision rule (MVN_DECIDE_*) used by this context's decode calls */
 int mvn_ctx_set_variant(mvn_ctx *ctx, int variant);
 int mvn_ctx_set_decision(mvn_ctx *ctx, int decision);

@@ -46,6 +46,8 @@ _PROTOS = {
     'mvn_ctx_destroy': (None, [c_void_p]),
     'mvn_ctx_set_vnet_weights_host': (c_int, [c_void_p] * 7),
     'mvn_ctx_vnet_decode_host': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
+    'mvn_ctx_vnet_decode_host_async': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
+    'mvn_ctx_synchronize': (c_int, [c_void_p]),
     'mvn_ctx_va_decode_host': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     'mvn_ctx_set_variant': (c_int, [c_void_p, c_int]),
     'mvn_ctx_set_decision': (c_int, [c_void_p, c_int]),

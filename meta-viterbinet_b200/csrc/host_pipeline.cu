@@ -25,7 +25,14 @@ struct mvn_ctx {
     cudaStream_t st[kSlots] = {};
     float *d_y[kSlots] = {};
     void *d_out[kSlots] = {};   // decoded words, or the targets of the evaluation forms
-    float *d_w = nullptr;       // packed w1,b1,w2,b2,w3,b3
+    static constexpr int kWSlots = 8;   // weight sets in flight (one per SNR point of a sweep): a ring, see set_vnet_weights
+    float *d_w = nullptr;       // kWSlots x packed w1,b1,w2,b2,w3,b3
+    int w_cur = -1;             // slot the next decode call reads
+    cudaStream_t st_w = nullptr;         // weight uploads (never queued behind a chunk)
+    cudaEvent_t w_ready[kWSlots] = {};   // upload of the slot finished
+    bool w_inflight[kWSlots] = {};       // launches enqueued since the last drain read the slot
+    int next_slot = 0;          // stream-ring position carried across asynchronous calls
+    bool pending = false;       // asynchronous work enqueued since the last mvn_ctx_synchronize
     float *d_sp = nullptr;      // state priors table (VA), up to sp_cap floats
     int64_t sp_cap = 0;
     double *d_taps = nullptr;   // taps of the on-device Monte-Carlo source
@@ -68,7 +75,9 @@ extern "C" int mvn_ctx_create(mvn_ctx **out, int device, int64_t chunk_frames, i
         if (e == cudaSuccess) e = cudaMalloc(&c->d_y[i], size_t(chunk_frames) * T_max * sizeof(float));
         if (e == cudaSuccess) e = cudaMalloc(&c->d_out[i], size_t(chunk_frames) * T_max * sizeof(float));
     }
-    if (e == cudaSuccess) e = cudaMalloc(&c->d_w, size_t(param_count(c->S)) * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_w, size_t(mvn_ctx::kWSlots) * param_count(c->S) * sizeof(float));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->st_w, cudaStreamNonBlocking);
+    for (int i = 0; i < mvn_ctx::kWSlots && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&c->w_ready[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_cnt, sizeof(unsigned long long) * 4 * mvn_ctx::kSlots);
     if (e != cudaSuccess) {
         mvn_ctx_destroy(c);
@@ -88,6 +97,12 @@ extern "C" void mvn_ctx_destroy(mvn_ctx *c) {
         if (c->st[i]) cudaStreamDestroy(c->st[i]);
     }
     if (c->d_w) cudaFree(c->d_w);
+    for (int i = 0; i < mvn_ctx::kWSlots; i++)
+        if (c->w_ready[i]) cudaEventDestroy(c->w_ready[i]);
+    if (c->st_w) {
+        cudaStreamSynchronize(c->st_w);
+        cudaStreamDestroy(c->st_w);
+    }
     if (c->d_sp) cudaFree(c->d_sp);
     if (c->d_taps) cudaFree(c->d_taps);
     if (c->d_cnt) cudaFree(c->d_cnt);
@@ -112,6 +127,12 @@ extern "C" int mvn_ctx_set_decision(mvn_ctx *c, int decision) {
     return MVN_OK;
 }
 
+static int drain(mvn_ctx *c, int rc);
+
+// The weights go to the NEXT slot of a ring, so that decode calls already enqueued (mvn_ctx_vnet_decode_host_async) keep
+// reading theirs: a sweep can stream point after point with different checkpoints without draining the pipeline in
+// between.  A slot that enqueued launches may still read is never overwritten: reaching it again (8 weight sets
+// without a synchronize in between) drains the pipeline first.
 extern "C" int mvn_ctx_set_vnet_weights_host(mvn_ctx *c, const float *w1, const float *b1, const float *w2,
                                              const float *b2, const float *w3, const float *b3) {
     if (!c || !w1 || !b1 || !w2 || !b2 || !w3 || !b3) {
@@ -119,14 +140,22 @@ extern "C" int mvn_ctx_set_vnet_weights_host(mvn_ctx *c, const float *w1, const 
         return MVN_ERR_ARG;
     }
     MVN_CUDA(cudaSetDevice(c->device));
+    const int slot = (c->w_cur + 1) % mvn_ctx::kWSlots;
+    if (c->w_inflight[slot]) {
+        const int rc = drain(c, MVN_OK);
+        if (rc != MVN_OK) return rc;
+    }
     const float *src[6] = {w1, b1, w2, b2, w3, b3};
     const int n[6] = {kH1, kH1, kH2 * kH1, kH2, c->S * kH2, c->S};
-    float *dst = c->d_w;
+    float *dst = c->d_w + size_t(slot) * param_count(c->S);
+    // pageable sources are staged by the runtime before the call returns; pinned ones must stay valid until the next sync
+    cudaStream_t st = c->st_w;
     for (int i = 0; i < 6; i++) {
-        MVN_CUDA(cudaMemcpyAsync(dst, src[i], size_t(n[i]) * sizeof(float), cudaMemcpyHostToDevice, c->st[0]));
+        MVN_CUDA(cudaMemcpyAsync(dst, src[i], size_t(n[i]) * sizeof(float), cudaMemcpyHostToDevice, st));
         dst += n[i];
     }
-    MVN_CUDA(cudaStreamSynchronize(c->st[0]));
+    MVN_CUDA(cudaEventRecord(c->w_ready[slot], st));
+    c->w_cur = slot;
     c->have_w = true;
     return MVN_OK;
 }
@@ -135,6 +164,7 @@ extern "C" int mvn_ctx_set_vnet_weights_host(mvn_ctx *c, const float *w1, const 
 // buffers) and reports the tcgen05 watchdog, so that a call whose pipeline timed out does not return MVN_OK.
 static int drain(mvn_ctx *c, int rc) {
     cudaError_t first = cudaSuccess;
+    for (int i = 0; i < mvn_ctx::kWSlots; i++) c->w_inflight[i] = false;
     for (int i = 0; i < mvn_ctx::kSlots; i++) {
         const cudaError_t e = cudaStreamSynchronize(c->st[i]);
         if (e != cudaSuccess && first == cudaSuccess) first = e;
@@ -159,7 +189,7 @@ static int drain(mvn_ctx *c, int rc) {
 // to y into the slot's d_out buffer (the targets of the evaluation form; then nothing is copied back per chunk).
 template <class Launch>
 static int run_pipeline(mvn_ctx *c, const float *y_host, const float *aux_host, int aux_T, int64_t B, int T, int out_format,
-                        void *decoded_host, Launch launch) {
+                        void *decoded_host, bool drain_at_end, Launch launch) {
     if (!c || !y_host || B < 0 || T < 1 || T > c->T_max) {
         set_error("host decode: bad argument (T=%d, T_max=%d)", T, c ? c->T_max : -1);
         return MVN_ERR_ARG;
@@ -167,7 +197,8 @@ static int run_pipeline(mvn_ctx *c, const float *y_host, const float *aux_host, 
     MVN_CUDA(cudaSetDevice(c->device));
     const int n_words = (T + 31) / 32;
     const size_t out_row = out_format == MVN_OUT_F32 ? size_t(T) * sizeof(float) : size_t(n_words) * sizeof(uint32_t);
-    int slot = 0;
+    int slot = c->next_slot;
+    c->pending = true;
     for (int64_t b0 = 0; b0 < B; b0 += c->chunk, slot = (slot + 1) % mvn_ctx::kSlots) {
         const int64_t nb = std::min<int64_t>(c->chunk, B - b0);
         cudaStream_t st = c->st[slot];
@@ -181,23 +212,63 @@ static int run_pipeline(mvn_ctx *c, const float *y_host, const float *aux_host, 
             MVN_PIPE(cudaMemcpyAsync(static_cast<char *>(decoded_host) + size_t(b0) * out_row, c->d_out[slot],
                                      size_t(nb) * out_row, cudaMemcpyDeviceToHost, st));
     }
-    return drain(c, MVN_OK);
+    c->next_slot = slot;
+    return drain_at_end ? drain(c, MVN_OK) : MVN_OK;
 }
 
-extern "C" int mvn_ctx_vnet_decode_host(mvn_ctx *c, const float *y_host, int64_t B, int T, int n_stages,
-                                        int out_format, void *decoded_host) {
+// every stream of the ring waits for the current weight slot's upload; afterwards the slot's last-use event is the join
+// of all ring streams (recorded on st[0] after it has waited for the others)
+static int weights_begin(mvn_ctx *c) {
+    for (int i = 0; i < mvn_ctx::kSlots; i++) MVN_CUDA(cudaStreamWaitEvent(c->st[i], c->w_ready[c->w_cur], 0));
+    return MVN_OK;
+}
+static int weights_end(mvn_ctx *c) {
+    c->w_inflight[c->w_cur] = true;
+    return MVN_OK;
+}
+
+static int vnet_decode_host_impl(mvn_ctx *c, const float *y_host, int64_t B, int T, int n_stages, int out_format,
+                                 void *decoded_host, bool drain_at_end) {
     if (!c || !c->have_w || !decoded_host) {
         set_error("mvn_ctx_vnet_decode_host: weights not set or no output buffer");
         return MVN_ERR_ARG;
     }
     const int S = c->S;
-    const float *w1 = c->d_w, *b1 = w1 + kH1, *w2 = b1 + kH1, *b2 = w2 + kH2 * kH1, *w3 = b2 + kH2, *b3 = w3 + S * kH2;
+    const float *w1 = c->d_w + size_t(c->w_cur) * param_count(S), *b1 = w1 + kH1, *w2 = b1 + kH1, *b2 = w2 + kH2 * kH1,
+                *w3 = b2 + kH2, *b3 = w3 + S * kH2;
     const int L = c->L, variant = c->variant, decision = c->decision;
-    return run_pipeline(c, y_host, nullptr, 0, B, T, out_format, decoded_host,
-                        [=](const float *dy, int64_t nb, void *dout, int64_t, int, cudaStream_t st) {
-                            return mvn_vnet_decode_ex(dy, nb, T, L, n_stages, w1, b1, w2, b2, w3, b3, out_format, dout,
-                                                      nullptr, nullptr, 0, 0, nullptr, variant, decision, st);
-                        });
+    MVN_CUDA(cudaSetDevice(c->device));
+    int rc = weights_begin(c);
+    if (rc != MVN_OK) return rc;
+    rc = run_pipeline(c, y_host, nullptr, 0, B, T, out_format, decoded_host, false,
+                      [=](const float *dy, int64_t nb, void *dout, int64_t, int, cudaStream_t st) {
+                          return mvn_vnet_decode_ex(dy, nb, T, L, n_stages, w1, b1, w2, b2, w3, b3, out_format, dout,
+                                                    nullptr, nullptr, 0, 0, nullptr, variant, decision, st);
+                      });
+    if (rc != MVN_OK) return rc;
+    rc = weights_end(c);
+    if (rc != MVN_OK) return drain(c, rc);
+    return drain_at_end ? drain(c, MVN_OK) : MVN_OK;
+}
+
+extern "C" int mvn_ctx_vnet_decode_host(mvn_ctx *c, const float *y_host, int64_t B, int T, int n_stages,
+                                        int out_format, void *decoded_host) {
+    return vnet_decode_host_impl(c, y_host, B, T, n_stages, out_format, decoded_host, true);
+}
+
+extern "C" int mvn_ctx_vnet_decode_host_async(mvn_ctx *c, const float *y_host, int64_t B, int T, int n_stages,
+                                              int out_format, void *decoded_host) {
+    return vnet_decode_host_impl(c, y_host, B, T, n_stages, out_format, decoded_host, false);
+}
+
+extern "C" int mvn_ctx_synchronize(mvn_ctx *c) {
+    if (!c) {
+        set_error("mvn_ctx_synchronize: bad argument");
+        return MVN_ERR_ARG;
+    }
+    MVN_CUDA(cudaSetDevice(c->device));
+    c->pending = false;
+    return drain(c, MVN_OK);
 }
 
 // sum the per-stream counter rows on the host: 6 x 32 bytes, one copy
@@ -233,10 +304,15 @@ extern "C" int mvn_ctx_vnet_eval_host(mvn_ctx *c, const float *y_host, const flo
     MVN_CUDA(cudaMemsetAsync(c->d_cnt, 0, sizeof(unsigned long long) * 4 * mvn_ctx::kSlots, c->st[0]));
     MVN_CUDA(cudaStreamSynchronize(c->st[0]));
     const int S = c->S;
-    const float *w1 = c->d_w, *b1 = w1 + kH1, *w2 = b1 + kH1, *b2 = w2 + kH2 * kH1, *w3 = b2 + kH2, *b3 = w3 + S * kH2;
+    const float *w1 = c->d_w + size_t(c->w_cur) * param_count(S), *b1 = w1 + kH1, *w2 = b1 + kH1, *b2 = w2 + kH2 * kH1,
+                *w3 = b2 + kH2, *b3 = w3 + S * kH2;
     const int L = c->L, variant = c->variant, decision = c->decision;
     unsigned long long *cnt = c->d_cnt;
-    const int rc = run_pipeline(c, y_host, target_host, target_T, B, T, out_format, nullptr,
+    {
+        const int rcw = weights_begin(c);
+        if (rcw != MVN_OK) return rcw;
+    }
+    const int rc = run_pipeline(c, y_host, target_host, target_T, B, T, out_format, nullptr, true,
                                 [=](const float *dy, int64_t nb, void *dtgt, int64_t, int slot, cudaStream_t st) {
                                     return mvn_vnet_decode_ex(dy, nb, T, L, n_stages, w1, b1, w2, b2, w3, b3, out_format,
                                                               nullptr, nullptr, static_cast<const float *>(dtgt), target_T,
@@ -272,7 +348,12 @@ extern "C" int mvn_ctx_vnet_sweep_point(mvn_ctx *c, int64_t B, int T, int n_stag
     MVN_CUDA(cudaMemsetAsync(c->d_cnt, 0, sizeof(unsigned long long) * 4 * mvn_ctx::kSlots, c->st[0]));
     MVN_CUDA(cudaStreamSynchronize(c->st[0]));
     const int S = c->S, L = c->L;
-    const float *w1 = c->d_w, *b1 = w1 + kH1, *w2 = b1 + kH1, *b2 = w2 + kH2 * kH1, *w3 = b2 + kH2, *b3 = w3 + S * kH2;
+    const float *w1 = c->d_w + size_t(c->w_cur) * param_count(S), *b1 = w1 + kH1, *w2 = b1 + kH1, *b2 = w2 + kH2 * kH1,
+                *w3 = b2 + kH2, *b3 = w3 + S * kH2;
+    {
+        const int rcw = weights_begin(c);
+        if (rcw != MVN_OK) return rcw;
+    }
     int slot = 0;
     for (int64_t b0 = 0; b0 < B; b0 += c->chunk, slot = (slot + 1) % mvn_ctx::kSlots) {
         const int64_t nb = std::min<int64_t>(c->chunk, B - b0);
@@ -318,7 +399,7 @@ extern "C" int mvn_ctx_va_decode_host(mvn_ctx *c, const float *y_host, int64_t B
     MVN_CUDA(cudaStreamSynchronize(c->st[0]));
     const float *dsp = c->d_sp;
     const int L = c->L, decision = c->decision;
-    return run_pipeline(c, y_host, nullptr, 0, B, T, out_format, decoded_host,
+    return run_pipeline(c, y_host, nullptr, 0, B, T, out_format, decoded_host, true,
                         [=](const float *dy, int64_t nb, void *dout, int64_t, int, cudaStream_t st) {
                             return mvn_va_decode_ex(dy, nb, T, L, n_stages, dsp, n_h, out_format, dout, nullptr, 0, 0,
                                                     nullptr, decision, st);

@@ -40,12 +40,15 @@ def all_reduce_counters(counters: torch.Tensor, group=None) -> torch.Tensor:
 
 def run_sweep(points: Sequence, frames_per_point: int,
               evaluate_block: Callable[[object, int, int, torch.Tensor], None],
-              device=None, rank: int = None, world_size: int = None, group=None) -> torch.Tensor:
+              device=None, rank: int = None, world_size: int = None, group=None,
+              before_reduce: Callable[[], None] = None) -> torch.Tensor:
     """Evaluate every point on `frames_per_point` frames, sharded over the ranks.
 
     evaluate_block(point, first_frame, n_frames, counters_row) must ADD the four counts of frames
     [first_frame, first_frame + n_frames) of that point into counters_row (an int64[4] view) — e.g. by
     calling ops.vnet_decode(..., target=..., counters=counters_row).
+    before_reduce() runs after this rank's last evaluate_block and before the all-reduce: a caller that spreads its
+    launches over several CUDA streams joins them there.
     Returns the all-reduced [len(points), 4] int64 tensor (identical on every rank).
     """
     if rank is None:
@@ -59,6 +62,8 @@ def run_sweep(points: Sequence, frames_per_point: int,
         rows = partition(frames_per_point, blocks, b)
         if len(rows):
             evaluate_block(points[i], rows.start, len(rows), counters[i])
+    if before_reduce is not None:
+        before_reduce()
     return all_reduce_counters(counters, group)
 
 

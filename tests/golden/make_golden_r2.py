@@ -76,6 +76,12 @@ def channel_fixture(tmp, torch, ce, VATrainer):
         out[f'{name}_meta'] = np.array([L, T, snr, tr.gamma, tr.noise_seed, tr.word_seed], dtype=np.float64)
         print(name, 'words', W, 'T', T)
     mg.save('channel', **out)
+    # the COST2100 tap magnitudes themselves (resources/cost2100_channel/h_{0..3}.mat, 300 blocks x 4 taps): input DATA of
+    # BASELINE.json configs[3], needed on the GPU box where the reference checkout does not exist
+    import scipy.io
+    taps = np.stack([scipy.io.loadmat(os.path.join(mg.REF, 'resources', 'cost2100_channel', f'h_{i}.mat'))['h_channel_response_mag'].reshape(-1)
+                     for i in range(4)], axis=1)
+    mg.save('cost2100_taps', taps=taps)
 
 
 def vnet4096_fixture(tmp, torch, VNETTrainer):
