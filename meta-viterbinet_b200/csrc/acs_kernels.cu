@@ -184,7 +184,7 @@ __device__ __forceinline__ float va_cost(float y, float sp) {
 }
 
 template <int L, int NT, bool MLSE>
-__global__ void __launch_bounds__(NT, (L <= 5 && !MLSE) ? 4 : 1) va_decode_kernel(VaParams p) {
+__global__ void __launch_bounds__(NT, (L <= 5) ? (MLSE ? 2 : 4) : 1) va_decode_kernel(VaParams p) {
     using D = TrellisDims<L>;
     constexpr int S = D::S, H = D::H, C = D::C, NCH = D::NCH;
     constexpr int WARPS = NT / 32;

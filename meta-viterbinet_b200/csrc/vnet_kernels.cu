@@ -88,6 +88,7 @@ struct VnetParams {
     int const_slot;
     int variant;           // MVN_VARIANT_*: which implementation runs (per call, no global state)
     int decision;          // MVN_DECIDE_*
+    int surv_words;        // MLSE: survivor words per frame (SurvStore<L>::words(n_stages))
 };
 
 // Variant = (frames per lane, weight source, threads per CTA, layer-2 unroll).  One CTA per SM.
@@ -327,10 +328,19 @@ __device__ long long g_tc_trace[64 * 32];
 #endif
 
 // tcgen05 variant (memory_length <= 6): every CTA stages its own weights (W2/b2 as bf16 pieces, the rest fp32).
-template <int L>
-static int launch_tc(VnetParams p, cudaStream_t st) {
-    const size_t smem = tc_smem_bytes<L>();
-    auto kern = vnet_decode_tc_kernel<L>;
+template <int L, bool MLSE>
+static int launch_tc_mode(VnetParams p, cudaStream_t st) {
+    size_t smem = tc_smem_bytes<L>();
+    if (MLSE) {
+        p.surv_words = SurvStore<L>::words(p.n_stages);
+        smem += size_t(tc::kConsWarps) * SurvStore<L>::bytes_per_warp(p.n_stages);
+        if (smem > 227 * 1024) {
+            set_error("mvn_vnet_decode (MLSE): %d stages of %d survivor bits do not fit the shared memory of one CTA",
+                      p.n_stages, SurvStore<L>::H);
+            return MVN_ERR_UNSUPPORTED;
+        }
+    }
+    auto kern = vnet_decode_tc_kernel<L, MLSE>;
     MVN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     p.n_warp_tiles = (p.B + 31) / 32;
     const int64_t need = (p.n_warp_tiles + 3) / 4;
@@ -356,6 +366,12 @@ static int launch_tc(VnetParams p, cudaStream_t st) {
     note_launch();
     MVN_CUDA(cudaGetLastError());
     return MVN_OK;
+}
+
+// tcgen05 variant (memory_length <= 6): every CTA stages its own weights (W2/b2 as fp16 pieces, the rest fp32).
+template <int L>
+static int launch_tc(const VnetParams &p, cudaStream_t st) {
+    return p.decision == MVN_DECIDE_REFERENCE ? launch_tc_mode<L, false>(p, st) : launch_tc_mode<L, true>(p, st);
 }
 
 // Default variants, picked by tools/tune_fused.py on a B200 (profiles/r01_tune_fused.txt):
@@ -473,8 +489,14 @@ extern "C" int mvn_vnet_decode_ex(const float *y, int64_t B, int T, int L, int n
         set_error("mvn_vnet_decode: unknown kernel variant %d", variant);
         return MVN_ERR_ARG;
     }
-    if (decision != MVN_DECIDE_REFERENCE) {
-        set_error("mvn_vnet_decode: decision mode %d not available", decision);
+    if (decision < MVN_DECIDE_REFERENCE || decision > MVN_DECIDE_MLSE_TERMINATED) {
+        set_error("mvn_vnet_decode: unknown decision mode %d", decision);
+        return MVN_ERR_ARG;
+    }
+    if (decision != MVN_DECIDE_REFERENCE && (L > 6 || variant == MVN_VARIANT_FMA_SMEM || variant == MVN_VARIANT_FMA_CONST320 ||
+                                             variant == MVN_VARIANT_FMA)) {
+        set_error("mvn_vnet_decode: the fused in-kernel traceback runs in the tensor-core kernel (memory_length <= 6, "
+                  "MVN_VARIANT_AUTO / MVN_VARIANT_TCGEN05); use mvn_vnet_priors + mvn_acs_decode + mvn_traceback otherwise");
         return MVN_ERR_UNSUPPORTED;
     }
     if (target && (!counters || target_T < 1 || target_T > T)) {
@@ -483,7 +505,7 @@ extern "C" int mvn_vnet_decode_ex(const float *y, int64_t B, int T, int L, int n
     }
     if (B == 0 || T == 0) return MVN_OK;
     VnetParams p{y, B, T, n_stages, VnetWeights{w1, b1, w2, b2, w3, b3}, out_format, decoded, priors_out, target,
-                 target_T, pilot_period, reinterpret_cast<unsigned long long *>(counters), 0, 0, variant, decision};
+                 target_T, pilot_period, reinterpret_cast<unsigned long long *>(counters), 0, 0, variant, decision, 0};
     return vnet_decode_impl(p, L, static_cast<cudaStream_t>(stream));
 }
 

@@ -281,7 +281,7 @@ __device__ __forceinline__ void h2_to_tmem(uint32_t slot_lane) {
 #define TC_TRACE(ev, cond) do {} while (0)
 #endif
 
-template <int L>
+template <int L, bool MLSE>
 __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch timeout_flag, long long *trace) {
     static_assert(L <= 6, "tcgen05 variant: the priors of one stage must fit a 64-column TMEM region");
     using D = TrellisDims<L>;
@@ -487,10 +487,18 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
             }
         }
     } else {
-        // consumers: priors of stage n -> ACS on the frame's private path metrics -> decision bit, outputs, BER
+        // consumers: priors of stage n -> ACS on the frame's private path metrics -> decision bit, outputs, BER.
+        // MLSE: no running decision; the S/2 survivor bits of every stage go to this warp's shared-memory masks and the
+        // frame is traced back in the kernel once its last stage is through (the producers are already two stages into the
+        // next tile by then, so the traceback overlaps their work).
         typename std::conditional<(L <= 5), RegTrellis<L>, SmemTrellis<L>>::type tr;
-        if constexpr (L > 5)   // path metrics of the 128 frames of the tile: [2][H][128] floats behind the W3 pieces
-            tr.init(reinterpret_cast<float *>(sB2 + kB2Bytes), 32 * tc::kConsWarps, quad * 32 + lane);
+        float *after_w3 = reinterpret_cast<float *>(sB2 + kB2Bytes);
+        if constexpr (L > 5) {  // path metrics of the 128 frames of the tile: [2][H][128] floats behind the W3 pieces
+            tr.init(after_w3, 32 * tc::kConsWarps, quad * 32 + lane);
+            after_w3 += SmemTrellis<L>::bytes(32 * tc::kConsWarps) / sizeof(float);
+        }
+        SurvStore<L> surv;
+        if constexpr (MLSE) surv.init(reinterpret_cast<uint32_t *>(after_w3) + size_t(quad) * p.surv_words * 32, lane);
         ErrAcc acc;
         constexpr int kConsFirst = tc::kProdWarps + tc::kConvWarps;
         for (int64_t ct = blockIdx.x; ct < n_cta_tiles; ct += gridDim.x) {
@@ -498,6 +506,19 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
             const int64_t b = row0 + lane;
             tr.reset();
             unsigned frame_bit_errs = 0;
+            auto emit = [&](int t0, uint32_t bits) {
+                if (p.decoded) {
+                    if (p.out_format == MVN_OUT_F32)
+                        warp_store_bits_f32(static_cast<float *>(p.decoded), p.B, p.T, p.T, row0, t0, bits, lane, vec_out);
+                    else if (b < p.B)
+                        static_cast<uint32_t *>(p.decoded)[b * n_words + t0 / 32] = bits;
+                }
+                if (p.target && t0 < p.target_T) {
+                    warp_load_tile(p.target, p.B, p.target_T, p.target_T, row0, t0, tile, lane, vec_tgt);
+                    frame_bit_errs += tile_bit_errors(tile + lane * kTileLd, bits, p.target_T - t0);
+                    __syncwarp();
+                }
+            };
             for (int t0 = 0; t0 < p.T; t0 += 32) {
                 uint32_t bits = 0;
                 const int t_end = min(32, p.n_stages - t0);
@@ -505,11 +526,12 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
                 for (int tt = 0; tt < t_end; tt++, n++) {
                     const uint32_t slot = n & 1, use = n >> 1;
                     const uint32_t ts = tmem + slot * tc::kSlotCols, slot_lane = ts + lane_base;
-                    bits |= tr.decide() << tt;                       // metrics entering this stage; overlaps the wait
+                    if constexpr (!MLSE) bits |= tr.decide() << tt;   // metrics entering this stage; overlaps the wait
                     tc::mbar_wait<MVN_CONS_PARK>(smem_addr(&d2_full[slot]), use & 1, timeout_flag);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     TC_TRACE(11, warp == kConsFirst && lane == 0);
                     float *dst = (p.priors_out && b < p.B) ? p.priors_out + (b * p.T + t0 + tt) * S : nullptr;
+                    uint32_t sv = 0;
                     // 16 source states per chunk: priors = D_main + D_corr / 2048, cost = -prior (vnet_detector.py:57)
                     auto chunk = [&](auto cc, bool last) {
                         constexpr int c = decltype(cc)::value;
@@ -529,8 +551,10 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
                             pr[i] = fmaf(pc_[i], tc::kInvScale, pm_[i]);
                             cost[i] = -pr[i];
                         }
-                        if constexpr (L <= 5) tr.template step_chunk<c>(cost);
-                        else tr.step_chunk_rt(c, cost);
+                        uint32_t s8;
+                        if constexpr (L <= 5) s8 = tr.template step_chunk<c>(cost);
+                        else s8 = tr.step_chunk_rt(c, cost);
+                        if constexpr (MLSE) sv |= s8 << (c * (C / 2));
                         if (dst) {
 #pragma unroll
                             for (int i = 0; i < C; i++) dst[c * C + i] = pr[i];
@@ -543,20 +567,18 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
                         chunk(std::integral_constant<int, 3>{}, true);
                     }
                     tr.commit();
+                    if constexpr (MLSE) surv.put(t0 + tt, sv, t0 + tt == p.n_stages - 1);
                     TC_TRACE(13, warp == kConsFirst && lane == 0);
                 }
                 __syncwarp();
-                if (p.decoded) {
-                    if (p.out_format == MVN_OUT_F32)
-                        warp_store_bits_f32(static_cast<float *>(p.decoded), p.B, p.T, p.T, row0, t0, bits, lane, vec_out);
-                    else if (b < p.B)
-                        static_cast<uint32_t *>(p.decoded)[b * n_words + t0 / 32] = bits;
-                }
-                if (p.target && t0 < p.target_T) {
-                    warp_load_tile(p.target, p.B, p.target_T, p.target_T, row0, t0, tile, lane, vec_tgt);
-                    frame_bit_errs += tile_bit_errors(tile + lane * kTileLd, bits, p.target_T - t0);
-                    __syncwarp();
-                }
+                if constexpr (!MLSE) emit(t0, bits);
+            }
+            if constexpr (MLSE) {
+                __syncwarp();
+                const int start = p.decision == MVN_DECIDE_MLSE_TERMINATED ? 0 : best_final_state<D::H>(tr);
+                for (int t0 = ((p.T - 1) / 32) * 32; t0 >= ((p.n_stages + 31) / 32) * 32; t0 -= 32) emit(t0, 0u);
+                traceback_frame<L>(surv, p.n_stages, start, [&](int tile_idx, uint32_t bits) { emit(tile_idx * 32, bits); });
+                __syncwarp();
             }
             if (p.target) {
                 const bool counted = b < p.B && !(p.pilot_period > 0 && b % p.pilot_period == 0);
@@ -576,7 +598,7 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
 }
 
 template <int L>
-constexpr size_t tc_smem_bytes() {
+constexpr size_t tc_smem_bytes() {   // + the consumers' survivor masks in MLSE mode (launch_tc)
     return size_t(tc::kBBytes) + tc::b2_bytes(1 << L) +
            (size_t(tc::kProdWarps + tc::kConsWarps) * kTileFloats + 4 * (tc::kK / 2)) * sizeof(float) +
            (L > 5 ? SmemTrellis<L>::bytes(32 * tc::kConsWarps) : 0);

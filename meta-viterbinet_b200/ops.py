@@ -147,9 +147,18 @@ def vnet_decode(y, weights, n_stages=None, out_format=OUT_F32, return_priors=Fal
         tT = tgt.shape[1]
         if counters is None:
             raise ValueError('target given without counters')
+    var = variant or _default_variant
+    if decision != 'reference' and (L > 6 or var not in ('auto', 'tcgen05')):
+        # the in-kernel traceback lives in the tensor-core kernel (memory_length <= 6); 128 / 256 states and the FP32-FMA
+        # variants take three launches: priors -> stage loop with exported survivors -> traceback kernel
+        pri = vnet_priors(y, ws)
+        dec = mlse_decode(-pri, n, terminated=(decision == 'mlse_terminated'), out_format=out_format)
+        if tgt is not None:
+            words = unpack_bits(dec, T) if out_format == OUT_BITS else dec
+            error_counts(words[:, :tT], tgt, pilot_period=pilot_period, counters=counters, want_rows=False)
+        return (dec, pri) if return_priors else dec
     check(load().mvn_vnet_decode_ex(ptr(y), B, T, L, n, *[ptr(w) for w in ws], out_format, ptr(dec), ptr(pri), ptr(tgt),
-                                    tT, pilot_period, ptr(counters), FUSED_VARIANTS[variant or _default_variant],
-                                    DECISIONS[decision], stream()))
+                                    tT, pilot_period, ptr(counters), FUSED_VARIANTS[var], DECISIONS[decision], stream()))
     return (dec, pri) if return_priors else dec
 
 
@@ -249,6 +258,8 @@ def mlse_decode(cost, n_stages=None, terminated=False, out_format=OUT_F32):
     B, T, S = cost.shape
     L = _mem_len(S)
     n = T if n_stages is None else int(n_stages)
+    if n == 0 or B == 0:                       # no stage: nothing to trace back, every column stays 0
+        return torch.zeros_like(_new_out(B, T, out_format, cost.device))
     _, pm, surv = acs_decode(cost, n, return_final_pm=True, return_survivors=True)
     dec = _new_out(B, T, out_format, cost.device)
     check(lib.mvn_traceback(ptr(surv), ptr(pm), B, T, n, L, 0 if terminated else -1, out_format, ptr(dec), stream()))

@@ -644,6 +644,33 @@ def test_va_fused_mlse_vs_oracle(mvn, L):
     assert np.array_equal(unpack_survivors(surv, H), orc.acs_decode(cost, return_survivors=True)[2][:, :, :H])
 
 
+@pytest.mark.parametrize('L', range(1, 9))
+def test_vnet_fused_mlse_vs_oracle(mvn, L):
+    """decision = MLSE inside the fused ViterbiNet kernel (tensor-core kernel, memory_length <= 6: survivor masks of the
+    consumer warps in shared memory, in-kernel traceback; 128 / 256 states: three launches): the bits are exactly the
+    oracle's traceback over the kernel's own exported priors, both start rules, ragged loops, packed output, counters."""
+    rng = np.random.RandomState(70 + L)
+    S = 2 ** L
+    w = [(rng.randn(*s) * sc).astype(np.float32) for s, sc in
+         [((100, 1), .7), ((100,), .5), ((50, 100), .15), ((50,), .1), ((S, 50), .3), ((S,), .1)]]
+    wd = [cu(a) for a in w]
+    for B, T, n_stages, term in ((130, 70, 70, False), (130, 70, 61, True), (257, 33, 33, True), (5, 40, 1, False), (64, 32, 0, True)):
+        y = (rng.randn(B, T) * 1.5).astype(np.float32)
+        tgt = rng.randint(0, 2, size=(B, T)).astype(np.float32)
+        cnt = mvn.ops.new_counters()
+        dec, pri = mvn.ops.vnet_decode(cu(y), wd, n_stages=n_stages, return_priors=True, target=cu(tgt), counters=cnt,
+                                       decision='mlse_terminated' if term else 'mlse')
+        dec, pri = dec.cpu().numpy(), pri.cpu().numpy()
+        ref = orc.mlse_decode(-pri, n_stages, 0 if term else -1)[0]
+        assert np.array_equal(dec, ref), (L, B, T, n_stages, term)
+        assert cnt.tolist() == [int((ref != tgt).sum()), int((ref != tgt).any(axis=1).sum()), B * T, B]
+    words = mvn.ops.vnet_decode(cu(y), wd, out_format=mvn.OUT_BITS, decision='mlse')
+    dec = mvn.ops.vnet_decode(cu(y), wd, decision='mlse')
+    assert torch.equal(mvn.ops.unpack_bits(words, T), dec)
+    f = mvn._lib.load().mvn_tc_timeout_status
+    assert f() == 0
+
+
 def test_va_fused_mlse_full_size(mvn):
     """2^20 frames x 120: replicas of 4096 oracle-decoded frames in shuffled order decode identically (one launch)"""
     from meta_viterbinet_b200.channel_taps import state_priors_table
