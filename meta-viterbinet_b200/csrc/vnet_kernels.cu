@@ -371,7 +371,13 @@ static int launch_tc_mode(VnetParams p, cudaStream_t st) {
 // tcgen05 variant (memory_length <= 6): every CTA stages its own weights (W2/b2 as fp16 pieces, the rest fp32).
 template <int L>
 static int launch_tc(const VnetParams &p, cudaStream_t st) {
-    return p.decision == MVN_DECIDE_REFERENCE ? launch_tc_mode<L, false>(p, st) : launch_tc_mode<L, true>(p, st);
+    if (p.decision == MVN_DECIDE_REFERENCE) return launch_tc_mode<L, false>(p, st);
+    if constexpr (L <= 6) {
+        return launch_tc_mode<L, true>(p, st);
+    } else {
+        set_error("vnet_decode (tcgen05): fused traceback is built for memory_length <= 6");
+        return MVN_ERR_UNSUPPORTED;
+    }
 }
 
 // Default variants, picked by tools/tune_fused.py on a B200 (profiles/r01_tune_fused.txt):
@@ -387,7 +393,7 @@ static int launch_tc(const VnetParams &p, cudaStream_t st) {
 template <int L>
 static int launch_fused(const VnetParams &p, cudaStream_t st) {
     const bool want_fma = p.variant == MVN_VARIANT_FMA_SMEM || p.variant == MVN_VARIANT_FMA_CONST320 || p.variant == MVN_VARIANT_FMA;
-    if constexpr (L <= 6) {
+    if constexpr (L <= 7) {
         if (!want_fma) return launch_tc<L>(p, st);  // auto and tcgen05
     }
     if constexpr (L <= 4) {
@@ -407,7 +413,7 @@ static int launch_fused(const VnetParams &p, cudaStream_t st) {
 
 // frames decoded by one full wave of CTAs (host pipeline chunk sizing)
 int vnet_frames_per_wave(int L, int variant) {
-    const int per_cta = (L <= 6 && !(variant == 1 || variant == 2 || variant == 4)) ? 128
+    const int per_cta = (L <= 7 && !(variant == 1 || variant == 2 || variant == 4)) ? 128
                         : L <= 3 ? 448 * 2 : L <= 5 ? 384 * 2 : L <= 7 ? 128 * 2 : 128;
     return per_cta * sm_count();
 }

@@ -81,6 +81,22 @@ __device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uin
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
         "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc));
 }
+// same with the accumulator read as D 2^-11 (scale-input-d): merges the scaled correction chain into the main chain on the
+// tensor core, D = A B + D / 2048
+__device__ __forceinline__ void mma_f16_ts_scale11(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p, 11;\n\t}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc));
+}
+// compile-time loop i = 0 .. N-1: f(integral_constant<int, i>)
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F &&f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
 __device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t (&v)[8]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(addr), "r"(v[0]),
                  "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]));
@@ -283,7 +299,11 @@ __device__ __forceinline__ void h2_to_tmem(uint32_t slot_lane) {
 
 template <int L, bool MLSE>
 __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch timeout_flag, long long *trace) {
-    static_assert(L <= 6, "tcgen05 variant: the priors of one stage must fit a 64-column TMEM region");
+    static_assert(L <= 7, "tcgen05 variant: the priors of one stage must fit the slot's 128 D columns");
+    // L <= 6: priors_main | priors_corr side by side in the slot's two 64-column D regions (one N = 2 N2 MMA per k-step).
+    // L == 7: 128 priors fill both regions, so the correction chain is computed first and folded into the main chain by
+    //         the tensor core itself (scale-input-d: D = A B + D 2^-11): ONE 128-column accumulator.
+    constexpr bool MERGED = (L == 7);
     using D = TrellisDims<L>;
     constexpr int S = D::S, C = D::C, NCH = D::NCH, NW = tc::kProdWarps + tc::kConvWarps + tc::kConsWarps;
     constexpr int N2 = tc::n2_of(S), kB2Bytes = tc::b2_bytes(S);
@@ -468,16 +488,34 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
                     TC_TRACE(8, warp == tc::kProdWarps && lane == 0);
                     asm volatile("bar.sync 2, %0;" ::"n"(32 * tc::kConvWarps));
                     TC_TRACE(9, warp == tc::kProdWarps && lane == 0);
-                    if (warp == tc::kProdWarps + 1 && tc::elect_one()) {  // one thread (not on the MMA warp's scheduler) issues layer 3: 4 + 4 MMAs
+                    if (warp == tc::kProdWarps + 1 && tc::elect_one()) {  // one thread (not on the MMA warp's scheduler) issues layer 3
                         asm volatile("tcgen05.fence::after_thread_sync;");
+                        if constexpr (!MERGED) {   // 4 + 4 MMAs
 #pragma unroll
-                        for (int j = 0; j < tc::kK2Steps; j++)   // priors_main | priors_corr = h2_hi [W3_hi | W3_lo]
-                            tc::mma_f16_ts(ts + tc::oDm, ts + tc::oAh + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2, kLBO2),
-                                           idesc2w, j > 0);
+                            for (int j = 0; j < tc::kK2Steps; j++)   // priors_main | priors_corr = h2_hi [W3_hi | W3_lo]
+                                tc::mma_f16_ts(ts + tc::oDm, ts + tc::oAh + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2, kLBO2),
+                                               idesc2w, j > 0);
 #pragma unroll
-                        for (int j = 0; j < tc::kK2Steps; j++)   // priors_corr += h2_lo W3_hi
-                            tc::mma_f16_ts(ts + tc::oDm + N2, ts + tc::oAl + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2, kLBO2),
-                                           idesc2, 1);
+                            for (int j = 0; j < tc::kK2Steps; j++)   // priors_corr += h2_lo W3_hi
+                                tc::mma_f16_ts(ts + tc::oDm + N2, ts + tc::oAl + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2, kLBO2),
+                                               idesc2, 1);
+                        } else {                   // 4 + 4 + 4 MMAs of N = 128 into one accumulator
+                            constexpr uint32_t kLoRows = (N2 / 8) * 128;   // byte offset of the W3_lo rows inside a k-chunk
+#pragma unroll
+                            for (int j = 0; j < tc::kK2Steps; j++)   // corr = h2_hi W3_lo
+                                tc::mma_f16_ts(ts + tc::oDm, ts + tc::oAh + j * 8,
+                                               tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2 + kLoRows, kLBO2), idesc2, j > 0);
+#pragma unroll
+                            for (int j = 0; j < tc::kK2Steps; j++)   // corr += h2_lo W3_hi
+                                tc::mma_f16_ts(ts + tc::oDm, ts + tc::oAl + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2, kLBO2),
+                                               idesc2, 1);
+                            // priors = h2_hi W3_hi + corr / 2048: the first MMA of the main chain reads D scaled by 2^-11
+                            tc::mma_f16_ts_scale11(ts + tc::oDm, ts + tc::oAh, tc::b_desc(sB2_addr, kLBO2), idesc2);
+#pragma unroll
+                            for (int j = 1; j < tc::kK2Steps; j++)
+                                tc::mma_f16_ts(ts + tc::oDm, ts + tc::oAh + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2, kLBO2),
+                                               idesc2, 1);
+                        }
                         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                             smem_addr(&d2_full[slot])));
                     }
@@ -533,11 +571,12 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
                     float *dst = (p.priors_out && b < p.B) ? p.priors_out + (b * p.T + t0 + tt) * S : nullptr;
                     uint32_t sv = 0;
                     // 16 source states per chunk: priors = D_main + D_corr / 2048, cost = -prior (vnet_detector.py:57)
-                    auto chunk = [&](auto cc, bool last) {
+                    auto chunk = [&](auto cc) {
                         constexpr int c = decltype(cc)::value;
+                        constexpr bool last = (c == NCH - 1);
                         float pm_[16], pc_[16];
                         tc::tmem_ld16(slot_lane + tc::oDm + 16 * c, pm_);
-                        tc::tmem_ld16(slot_lane + tc::oDm + N2 + 16 * c, pc_);
+                        if constexpr (!MERGED) tc::tmem_ld16(slot_lane + tc::oDm + N2 + 16 * c, pc_);
                         asm volatile("tcgen05.wait::ld.sync.aligned;");
                         if (last) {
                             asm volatile("tcgen05.fence::before_thread_sync;");
@@ -548,24 +587,19 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
                         float pr[C], cost[C];
 #pragma unroll
                         for (int i = 0; i < C; i++) {
-                            pr[i] = fmaf(pc_[i], tc::kInvScale, pm_[i]);
+                            pr[i] = MERGED ? pm_[i] : fmaf(pc_[i], tc::kInvScale, pm_[i]);
                             cost[i] = -pr[i];
                         }
                         uint32_t s8;
                         if constexpr (L <= 5) s8 = tr.template step_chunk<c>(cost);
                         else s8 = tr.step_chunk_rt(c, cost);
-                        if constexpr (MLSE) sv |= s8 << (c * (C / 2));
+                        if constexpr (MLSE) sv |= s8 << ((c * (C / 2)) & 31);
                         if (dst) {
 #pragma unroll
                             for (int i = 0; i < C; i++) dst[c * C + i] = pr[i];
                         }
                     };
-                    chunk(std::integral_constant<int, 0>{}, NCH == 1);
-                    if constexpr (NCH >= 2) chunk(std::integral_constant<int, 1>{}, NCH == 2);
-                    if constexpr (NCH >= 4) {
-                        chunk(std::integral_constant<int, 2>{}, false);
-                        chunk(std::integral_constant<int, 3>{}, true);
-                    }
+                    tc::static_for<0, NCH>(chunk);
                     tr.commit();
                     if constexpr (MLSE) surv.put(t0 + tt, sv, t0 + tt == p.n_stages - 1);
                     TC_TRACE(13, warp == kConsFirst && lane == 0);
