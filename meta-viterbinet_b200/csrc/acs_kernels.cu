@@ -61,96 +61,263 @@ __device__ __forceinline__ uint32_t step_chunk_any(TrellisFor<L> &tr, int c, con
     }
 }
 
+// Tiles of the [B, T*S] cost matrix stream through a per-warp ring of kAcsBuf buffers filled with cp.async: a warp keeps
+// kAcsBuf - 1 tiles (4 KB each) in flight while it consumes the oldest, across the boundary between its frame tiles, so the
+// kernel is bound by HBM and not by the latency of one tile at a time (which is what limited the 64..256-state trellises,
+// where the path metrics in shared memory allow only four warps per SM).
+constexpr int kAcsBuf = 4;
+
 template <int L, int NT>
-__global__ void __launch_bounds__(NT, (L <= 5) ? 4 : 1) acs_decode_kernel(AcsParams p) {
+__global__ void __launch_bounds__(NT, (L <= 5) ? 4 : (L == 6) ? 3 : 1) acs_decode_kernel(AcsParams p) {
     using D = TrellisDims<L>;
     constexpr int S = D::S, H = D::H, C = D::C, NCH = D::NCH;
     constexpr int WARPS = NT / 32;
     constexpr int SW = (H + 31) / 32;  // survivor words per stage
+    constexpr int SPT = (S <= 32) ? 32 / S : 1;   // stages per tile
+    constexpr int TPS = (S <= 32) ? 1 : S / 32;   // tiles per stage
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float *tile = smem + warp * kTileFloats;
-    const float *row = tile + lane * kTileLd;
+    float *ring = smem + warp * (kAcsBuf * kTileFloats);
 
     TrellisFor<L> tr;
-    if constexpr (L > kRegTrellisMaxL) tr.init(smem + WARPS * kTileFloats, NT, threadIdx.x);
+    if constexpr (L > kRegTrellisMaxL) tr.init(smem + WARPS * kAcsBuf * kTileFloats, NT, threadIdx.x);
 
     const int64_t ld = int64_t(p.T) * S;
     const bool vec_in = is_vec_ok(p.cost, ld, ld);
     const bool vec_out = p.out_format == MVN_OUT_F32 && is_vec_ok(p.decoded, p.T, p.T);
     const int n_words = (p.T + 31) / 32;
+    const int KT = (S <= 32) ? (p.n_stages + SPT - 1) / SPT : p.n_stages * TPS;   // tiles per frame tile
+    const int64_t wt0 = int64_t(blockIdx.x) * WARPS + warp, wt_step = int64_t(gridDim.x) * WARPS;
+    const int64_t my_tiles = wt0 < p.n_warp_tiles ? (p.n_warp_tiles - wt0 + wt_step - 1) / wt_step : 0;
+    const int64_t total = my_tiles * KT;          // flat sequence of this warp's cost tiles
 
-    for (int64_t wt = int64_t(blockIdx.x) * WARPS + warp; wt < p.n_warp_tiles; wt += int64_t(gridDim.x) * WARPS) {
-        const int64_t row0 = wt * 32;
+    auto issue = [&](int64_t idx) {               // tile idx of the flat sequence -> ring slot idx % kAcsBuf
+        if (idx < total) {
+            const int64_t wt = wt0 + (idx / KT) * wt_step;
+            const int k = int(idx % KT);
+            warp_load_tile_async(p.cost, p.B, ld, ld, wt * 32, int64_t(k) * 32, ring + (idx % kAcsBuf) * kTileFloats, lane);
+        } else {
+            cp_async_commit_empty();
+        }
+    };
+    if (vec_in)
+        for (int i = 0; i < kAcsBuf - 1; i++) issue(i);
+
+    int64_t idx = 0;
+    for (int64_t j = 0; j < my_tiles; j++) {
+        const int64_t row0 = (wt0 + j * wt_step) * 32;
         const int64_t b = row0 + lane;
         tr.reset();
-        for (int t0 = 0; t0 < p.T; t0 += 32) {
-            uint32_t bits = 0;
-            const int t_end = min(32, p.n_stages - t0);
-            int tt = 0;
-            while (tt < t_end) {
-                if constexpr (S <= 32) {
-                    constexpr int SPT = 32 / S;  // stages per staged tile
-                    warp_load_tile(p.cost, p.B, ld, ld, row0, int64_t(t0 + tt) * S, tile, lane, vec_in);
+        uint32_t bits = 0;
+        uint32_t sv = 0;
+        for (int k = 0; k < KT; k++, idx++) {
+            float *tile = ring + (idx % kAcsBuf) * kTileFloats;
+            if (vec_in) {
+                issue(idx + kAcsBuf - 1);          // refills the slot consumed in the previous iteration
+                cp_async_wait<kAcsBuf - 1>();
+                __syncwarp();
+            } else {
+                warp_load_tile(p.cost, p.B, ld, ld, row0, int64_t(k) * 32, tile, lane, false);
+            }
+            const float *row = tile + lane * kTileLd;
+            if constexpr (S <= 32) {
 #pragma unroll
-                    for (int u = 0; u < SPT; u++) {
-                        if (tt < t_end) {
-                            bits |= tr.decide() << tt;
-                            float c0[C];
+                for (int u = 0; u < SPT; u++) {
+                    const int t = k * SPT + u;
+                    if (t < p.n_stages) {
+                        bits |= tr.decide() << (t & 31);
+                        float c0[C];
 #pragma unroll
-                            for (int i = 0; i < C; i++) c0[i] = row[u * S + i];
-                            uint32_t sv = tr.template step_chunk<0>(c0);
-                            if constexpr (NCH == 2) {
-                                float c1[C];
+                        for (int i = 0; i < C; i++) c0[i] = row[u * S + i];
+                        uint32_t s1 = tr.template step_chunk<0>(c0);
+                        if constexpr (NCH == 2) {
+                            float c1[C];
 #pragma unroll
-                                for (int i = 0; i < C; i++) c1[i] = row[u * S + C + i];
-                                sv |= tr.template step_chunk<1>(c1) << (C / 2);
+                            for (int i = 0; i < C; i++) c1[i] = row[u * S + C + i];
+                            s1 |= tr.template step_chunk<1>(c1) << (C / 2);
+                        }
+                        tr.commit();
+                        if (p.survivors && b < p.B) p.survivors[(b * p.n_stages + t) * SW] = s1;
+                        if ((t & 31) == 31 || t == p.n_stages - 1) {
+                            // (the store below contains shuffles: t is warp-uniform)
+                            if (p.decoded) {
+                                if (p.out_format == MVN_OUT_F32)
+                                    warp_store_bits_f32(static_cast<float *>(p.decoded), p.B, p.T, p.T, row0, (t >> 5) * 32, bits,
+                                                        lane, vec_out);
+                                else if (b < p.B)
+                                    static_cast<uint32_t *>(p.decoded)[b * n_words + (t >> 5)] = bits;
                             }
-                            tr.commit();
-                            if (p.survivors && b < p.B) p.survivors[(b * p.n_stages + t0 + tt) * SW] = sv;
-                            tt++;
+                            bits = 0;
                         }
                     }
-                    __syncwarp();
-                } else {
-                    constexpr int TPS = S / 32;  // staged tiles per stage
-                    bits |= tr.decide() << tt;
-                    uint32_t sv = 0;
-#pragma unroll(L <= kRegTrellisMaxL ? TPS : 1)
-                    for (int k = 0; k < TPS; k++) {
-                        warp_load_tile(p.cost, p.B, ld, ld, row0, int64_t(t0 + tt) * S + 32 * k, tile, lane, vec_in);
+                }
+            } else {
+                const int t = k / TPS, part = k % TPS;
+                if (part == 0) bits |= tr.decide() << (t & 31);
 #pragma unroll
-                        for (int u = 0; u < 2; u++) {
-                            float cc[C];
+                for (int u = 0; u < 2; u++) {
+                    float cc[C];
 #pragma unroll
-                            for (int i = 0; i < C; i++) cc[i] = row[u * C + i];
-                            const int c = 2 * k + u;
-                            const uint32_t s8 = step_chunk_any<L>(tr, c, cc);
-                            sv |= s8 << ((c * 8) & 31);
-                            if ((c & 3) == 3 || c == NCH - 1) {
-                                if (p.survivors && b < p.B)
-                                    p.survivors[(b * p.n_stages + t0 + tt) * SW + (c * 8) / 32] = sv;
-                                sv = 0;
-                            }
-                        }
-                        __syncwarp();
+                    for (int i = 0; i < C; i++) cc[i] = row[u * C + i];
+                    const int c = 2 * part + u;
+                    const uint32_t s8 = step_chunk_any<L>(tr, c, cc);
+                    sv |= s8 << ((c * 8) & 31);
+                    if ((c & 3) == 3 || c == NCH - 1) {
+                        if (p.survivors && b < p.B) p.survivors[(b * p.n_stages + t) * SW + (c * 8) / 32] = sv;
+                        sv = 0;
                     }
+                }
+                if (part == TPS - 1) {
                     tr.commit();
-                    tt++;
+                    if ((t & 31) == 31 || t == p.n_stages - 1) {
+                        if (p.decoded) {
+                            if (p.out_format == MVN_OUT_F32)
+                                warp_store_bits_f32(static_cast<float *>(p.decoded), p.B, p.T, p.T, row0, (t >> 5) * 32, bits, lane,
+                                                    vec_out);
+                            else if (b < p.B)
+                                static_cast<uint32_t *>(p.decoded)[b * n_words + (t >> 5)] = bits;
+                        }
+                        bits = 0;
+                    }
                 }
             }
-            if (p.decoded) {
-                if (p.out_format == MVN_OUT_F32)
-                    warp_store_bits_f32(static_cast<float *>(p.decoded), p.B, p.T, p.T, row0, t0, bits, lane, vec_out);
-                else if (b < p.B)
-                    static_cast<uint32_t *>(p.decoded)[b * n_words + t0 / 32] = bits;
-            }
+            __syncwarp();   // every lane is done with this ring slot before it is refilled
         }
+        // output words past the stage loop stay 0 (decoded_word = zeros(y.shape), va_detector.py:89)
+        if (p.decoded)
+            for (int t0 = ((p.n_stages + 31) / 32) * 32; t0 < p.T; t0 += 32) {
+                if (p.out_format == MVN_OUT_F32)
+                    warp_store_bits_f32(static_cast<float *>(p.decoded), p.B, p.T, p.T, row0, t0, 0u, lane, vec_out);
+                else if (b < p.B)
+                    static_cast<uint32_t *>(p.decoded)[b * n_words + t0 / 32] = 0u;
+            }
         if (p.final_pm && b < p.B) {
             for (int h = 0; h < H; h++) {
                 const float v = tr.metric(h);
                 p.final_pm[b * S + h] = v;
                 if (S > 1) p.final_pm[b * S + h + H] = v;
+            }
+        }
+    }
+    if (vec_in) cp_async_wait<0>();
+}
+
+// =====================================================================================
+// a3 for 64..256 states, STATES ON LANES: one warp owns one frame, lane l keeps the R = S/64 distinct path metrics
+// pm[R l .. R l + R) in registers.  The reference trellis makes this layout shuffle-light: the two sources of new state j
+// are 2j and 2j+1, i.e. ADJACENT metrics, and source s and s + S/2 share a metric, so a lane adds its R metrics to the 2R
+// branch costs it loaded straight from HBM (two coalesced vector loads per lane and stage, no shared-memory staging), takes
+// the pairwise minima locally (R >= 2) and the warp only has to re-deal the results: new[R l' + i] comes from the low halves
+// of lanes 2l', 2l'+1 for l' < 16 and from the high halves of lanes 2(l'-16), 2(l'-16)+1 above (2R shuffles per stage).
+// The decision (lowest state attaining the minimum, & 1) is one REDUX.MIN on order-preserving integer keys + a ballot.
+// No per-frame shared memory at all, so the SMs run 48+ warps each and the kernel is bound by HBM, not by the latency of
+// four lone warps walking shared-memory path metrics (what limited the lane-per-frame form at 128 / 256 states).
+// =====================================================================================
+__device__ __forceinline__ uint32_t order_key(float v) {   // monotone float -> uint map (+0 and -0 collapse first)
+    const uint32_t u = __float_as_uint(v + 0.f);
+    return u ^ ((u >> 31) ? 0xffffffffu : 0x80000000u);
+}
+
+template <int L>
+__global__ void __launch_bounds__(256) acs_decode_warp_kernel(AcsParams p) {
+    static_assert(L >= 6 && L <= 8, "states-on-lanes layout: 64..256 states");
+    constexpr int S = 1 << L, H = S / 2, R = H / 32;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+    const int n_words = (p.T + 31) / 32;
+    const bool lower = lane < 16;
+    const int src = lower ? 2 * lane : 2 * (lane - 16);   // lanes whose results this lane collects
+    for (int64_t b = warp_global; b < p.B; b += n_warps) {
+        const float *cost = p.cost + b * int64_t(p.T) * S;
+        float pm[R];
+#pragma unroll
+        for (int i = 0; i < R; i++) pm[i] = 0.f;
+        uint32_t bits = 0;
+        auto load = [&](int t, float (&lo)[R], float (&hi)[R]) {   // branch costs of sources R l + i and H + R l + i
+            const float *c = cost + int64_t(t) * S + R * lane;
+            if constexpr (R == 4) {
+                const float4 a = ldg_stream4(c), d = ldg_stream4(c + H);
+                lo[0] = a.x, lo[1] = a.y, lo[2] = a.z, lo[3] = a.w, hi[0] = d.x, hi[1] = d.y, hi[2] = d.z, hi[3] = d.w;
+            } else if constexpr (R == 2) {
+                const float2 a = ldg_stream2(c), d = ldg_stream2(c + H);
+                lo[0] = a.x, lo[1] = a.y, hi[0] = d.x, hi[1] = d.y;
+            } else {
+                lo[0] = ldg_stream1(c);
+                hi[0] = ldg_stream1(c + H);
+            }
+        };
+        constexpr int U = 4;   // stages in flight per warp (8 was slower at 128 states: registers cost resident warps)
+        float clo[U][R], chi[U][R];
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (u < p.n_stages) load(u, clo[u], chi[u]);
+        for (int t0 = 0; t0 < p.n_stages; t0 += U) {
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int t = t0 + u;
+                if (t < p.n_stages) {
+                    // ---- decision on the metrics entering stage t
+                    uint32_t kmin = order_key(pm[0]), par = (R == 1) ? uint32_t(lane & 1) : 0u;
+#pragma unroll
+                    for (int i = 1; i < R; i++) {
+                        const uint32_t k = order_key(pm[i]);
+                        if (k < kmin) {
+                            kmin = k;
+                            par = uint32_t(i & 1);
+                        }
+                    }
+                    const uint32_t m = __reduce_min_sync(kFull, kmin);
+                    const uint32_t who = __ballot_sync(kFull, kmin == m);
+                    bits |= __shfl_sync(kFull, par, __ffs(who) - 1) << (t & 31);
+                    // ---- ACS
+                    float nlo[R >= 2 ? R / 2 : 1], nhi[R >= 2 ? R / 2 : 1];
+                    if constexpr (R >= 2) {
+#pragma unroll
+                        for (int k = 0; k < R / 2; k++) {
+                            nlo[k] = fminf(pm[2 * k] + clo[u][2 * k], pm[2 * k + 1] + clo[u][2 * k + 1]);
+                            nhi[k] = fminf(pm[2 * k] + chi[u][2 * k], pm[2 * k + 1] + chi[u][2 * k + 1]);
+                        }
+#pragma unroll
+                        for (int i = 0; i < R; i++) {   // new[R l' + i]: element i % (R/2) of lane src + i / (R/2)
+                            const float a = __shfl_sync(kFull, nlo[i % (R / 2)], src + i / (R / 2));
+                            const float c = __shfl_sync(kFull, nhi[i % (R / 2)], src + i / (R / 2));
+                            pm[i] = lower ? a : c;
+                        }
+                    } else {
+                        const float tl = pm[0] + clo[u][0], th = pm[0] + chi[u][0];
+                        const float a = fminf(__shfl_sync(kFull, tl, src), __shfl_sync(kFull, tl, src + 1));
+                        const float c = fminf(__shfl_sync(kFull, th, src), __shfl_sync(kFull, th, src + 1));
+                        pm[0] = lower ? a : c;
+                    }
+                    if (t + U < p.n_stages) load(t + U, clo[u], chi[u]);
+                    if ((t & 31) == 31 || t == p.n_stages - 1) {
+                        if (p.decoded) {
+                            if (p.out_format == MVN_OUT_F32) {
+                                const int col = (t & ~31) + lane;
+                                if (col < p.T) static_cast<float *>(p.decoded)[b * p.T + col] = float((bits >> lane) & 1u);
+                            } else if (lane == 0) {
+                                static_cast<uint32_t *>(p.decoded)[b * n_words + (t >> 5)] = bits;
+                            }
+                        }
+                        bits = 0;
+                    }
+                }
+            }
+        }
+        if (p.decoded)   // columns past the stage loop stay 0
+            for (int t0 = ((p.n_stages + 31) / 32) * 32; t0 < p.T; t0 += 32) {
+                if (p.out_format == MVN_OUT_F32) {
+                    if (t0 + lane < p.T) static_cast<float *>(p.decoded)[b * p.T + t0 + lane] = 0.f;
+                } else if (lane == 0) {
+                    static_cast<uint32_t *>(p.decoded)[b * n_words + t0 / 32] = 0u;
+                }
+            }
+        if (p.final_pm) {
+#pragma unroll
+            for (int i = 0; i < R; i++) {
+                p.final_pm[b * S + R * lane + i] = pm[i];
+                p.final_pm[b * S + H + R * lane + i] = pm[i];
             }
         }
     }
@@ -331,8 +498,23 @@ __global__ void __launch_bounds__(NT, (L <= 5) ? (MLSE ? 2 : 4) : 1) va_decode_k
 // =====================================================================================
 template <int L>
 static int launch_acs(const AcsParams &p, cudaStream_t st) {
-    constexpr int NT = (L <= 5) ? 256 : 128;
-    size_t smem = size_t(NT / 32) * kTileFloats * sizeof(float);
+    if constexpr (L >= 7) {   // (at 64 states the lane-per-frame kernel with its register trellis is faster: 63 % vs 39 % of HBM)
+        // states on lanes (one warp per frame) unless the survivor export is wanted (that stays with the lane-per-frame
+        // kernel, which assembles the bit masks per lane); needs 16-byte aligned rows for the vector loads at 256 states
+        if (!p.survivors && (reinterpret_cast<uintptr_t>(p.cost) & 15u) == 0) {
+            auto kern = acs_decode_warp_kernel<L>;
+            int per_sm = 1;
+            MVN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
+            if (per_sm < 1) per_sm = 1;
+            const int grid = int(std::min<int64_t>((p.B + 7) / 8, int64_t(sm_count()) * per_sm));
+            kern<<<grid, 256, 0, st>>>(p);
+            note_launch();
+            MVN_CUDA(cudaGetLastError());
+            return MVN_OK;
+        }
+    }
+    constexpr int NT = 128;
+    size_t smem = size_t(NT / 32) * kAcsBuf * kTileFloats * sizeof(float);
     if (L > kRegTrellisMaxL) smem += SmemTrellis<L>::bytes(NT);
     auto kern = acs_decode_kernel<L, NT>;
     MVN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));

@@ -49,6 +49,11 @@ __device__ __forceinline__ float4 ldg_stream4(const float *p) {
                  : "l"(p));
     return v;
 }
+__device__ __forceinline__ float2 ldg_stream2(const float *p) {
+    float2 v;
+    asm volatile("ld.global.nc.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ float ldg_stream1(const float *p) {
     float v;
     asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
@@ -87,6 +92,29 @@ __device__ __forceinline__ void warp_load_tile(const float *__restrict__ src, in
         }
     }
     __syncwarp();
+}
+
+// Asynchronous form of the vectorised tile load (cp.async, SASS LDGSTS): the copies of one tile form one commit group, so
+// a warp can keep several tiles in flight and wait for the oldest only (cp_async_wait<N>, then __syncwarp).  Needs the
+// vec conditions of warp_load_tile; out-of-range elements are zero-filled (src-size 0).
+__device__ __forceinline__ void warp_load_tile_async(const float *__restrict__ src, int64_t nrows, int64_t ld, int64_t ncols,
+                                                     int64_t row0, int64_t c0, float *tile, int lane) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int r = 4 * i + (lane >> 3);
+        const int c = (lane & 7) * 4;
+        const int64_t row = row0 + r;
+        const bool ok = row < nrows && c0 + c < ncols;
+        const float *g = ok ? src + row * ld + c0 + c : src;
+        const uint32_t dst = uint32_t(__cvta_generic_to_shared(tile + r * kTileLd + c));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(g), "r"(ok ? 16 : 0) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void cp_async_commit_empty() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
 // Each lane holds a 32-step decision mask for row row0+lane; the warp writes them as fp32 0/1

@@ -101,6 +101,30 @@ def test_acs_block_matches(mvn, L):
     assert np.array_equal(val1.cpu().numpy(), orc.acs_stage(pm, np.broadcast_to(c[:, :1], pm.shape))[0])
 
 
+@pytest.mark.parametrize('L', [6, 7, 8])
+def test_acs_decode_states_on_lanes(mvn, L):
+    """128 / 256 states run one warp per frame with the states on the lanes (registers + shuffles, costs straight from
+    HBM); without the survivor export that is the kernel mvn_acs_decode launches: bits and final metrics bit-exact vs the
+    oracle, random and exact-tie costs, ragged loop lengths, both output formats; and identical to the lane-per-frame
+    kernel (which the survivor export selects)."""
+    rng = np.random.RandomState(300 + L)
+    S, B, T = 2 ** L, 77, 45
+    cost = (rng.randn(B, T, S) * 2).astype(np.float32)
+    cost[::3] = rng.randint(0, 3, size=cost[::3].shape)        # exact ties
+    cost[1] = 0.0
+    cost[2] = -0.0
+    for n in (T, T - 13, 32, 1, 0):
+        ref, pm_ref = orc.acs_decode(cost, n)
+        dec, pm = mvn.ops.acs_decode(cu(cost), n, return_final_pm=True)
+        assert np.array_equal(dec.cpu().numpy(), ref), (L, n)
+        assert np.array_equal(pm.cpu().numpy(), pm_ref), (L, n)
+        words = mvn.ops.acs_decode(cu(cost), n, out_format=mvn.OUT_BITS)
+        assert np.array_equal(mvn.ops.unpack_bits(words, T).cpu().numpy(), ref)
+        if n > 0:
+            dec2, _, _ = mvn.ops.acs_decode(cu(cost), n, return_final_pm=True, return_survivors=True)
+            assert torch.equal(dec2, dec)
+
+
 # ------------------------------------------------------------------------------- a4/a5 VA
 VA_CASES = ['L4_fade1_ecc', 'L4_fade2', 'L4_cost2100_ecc'] + [f'L{L}_static' for L in (3, 5, 6, 7, 8)]
 
