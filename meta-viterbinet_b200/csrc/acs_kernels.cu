@@ -65,10 +65,11 @@ __device__ __forceinline__ uint32_t step_chunk_any(TrellisFor<L> &tr, int c, con
 // kAcsBuf - 1 tiles (4 KB each) in flight while it consumes the oldest, across the boundary between its frame tiles, so the
 // kernel is bound by HBM and not by the latency of one tile at a time (which is what limited the 64..256-state trellises,
 // where the path metrics in shared memory allow only four warps per SM).
-constexpr int kAcsBuf = 4;
+template <int L> struct AcsCfg { static constexpr int NT = (L <= 5) ? 256 : 128, NBUF = (L <= 5) ? 2 : 4; };
 
 template <int L, int NT>
-__global__ void __launch_bounds__(NT, (L <= 5) ? 4 : (L == 6) ? 3 : 1) acs_decode_kernel(AcsParams p) {
+__global__ void __launch_bounds__(NT, (L <= 5) ? 3 : (L == 6) ? 3 : 1) acs_decode_kernel(AcsParams p) {
+    constexpr int kAcsBuf = AcsCfg<L>::NBUF;
     using D = TrellisDims<L>;
     constexpr int S = D::S, H = D::H, C = D::C, NCH = D::NCH;
     constexpr int WARPS = NT / 32;
@@ -513,8 +514,8 @@ static int launch_acs(const AcsParams &p, cudaStream_t st) {
             return MVN_OK;
         }
     }
-    constexpr int NT = 128;
-    size_t smem = size_t(NT / 32) * kAcsBuf * kTileFloats * sizeof(float);
+    constexpr int NT = AcsCfg<L>::NT;
+    size_t smem = size_t(NT / 32) * AcsCfg<L>::NBUF * kTileFloats * sizeof(float);
     if (L > kRegTrellisMaxL) smem += SmemTrellis<L>::bytes(NT);
     auto kern = acs_decode_kernel<L, NT>;
     MVN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
