@@ -70,6 +70,12 @@ int mvn_vnet_priors_backward2(const float *y, int64_t N, int L, const float *the
 int mvn_vnet_detect_batched(const float *theta, int R, int L, const float *y, int T, int n_stages, float *decoded,
                             float *priors_out, void *stream);
 
+/* Same kernel with ONE weight set shared by all B words: the single-launch form of VNETDetector.forward(y, 'val') for
+ * batches too small to fill the GPU with the frame-per-lane kernels (B = 1 in eval_by_word, trainer.py:295; B = 300 in the
+ * aggregated evaluation of plotter_main.py:96-111).  theta [P] packed in torch parameter order; memory_length 1..5. */
+int mvn_vnet_detect_small(const float *theta, int64_t B, int L, const float *y, int T, int n_stages, float *decoded,
+                          float *priors_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

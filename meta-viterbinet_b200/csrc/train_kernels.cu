@@ -496,8 +496,8 @@ __global__ void __launch_bounds__(kTrainThreads, 1) priors_backward2_kernel(cons
 // priors this kernel computes (and optionally exports).
 // ---------------------------------------------------------------------------------------------
 template <int L>
-__global__ void __launch_bounds__(kTrainThreads, 1) detect_batched_kernel(const float *__restrict__ theta_all, int R,
-                                                                         const float *__restrict__ y, int T, int n_stages,
+__global__ void __launch_bounds__(kTrainThreads, 1) detect_batched_kernel(const float *__restrict__ theta_all, int theta_stride,
+                                                                         int R, const float *__restrict__ y, int T, int n_stages,
                                                                          float *__restrict__ decoded,
                                                                          float *__restrict__ priors_out) {
     constexpr int S = 1 << L;
@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1) detect_batched_kernel(const 
     extern __shared__ __align__(16) float sm[];
     float *th = sm, *pri = sm + PP;  // pri[256][S]
     for (int r = blockIdx.x; r < R; r += gridDim.x) {
-        for (int i = threadIdx.x; i < P; i += kTrainThreads) th[i] = theta_all[size_t(r) * P + i];
+        for (int i = threadIdx.x; i < P; i += kTrainThreads) th[i] = theta_all[size_t(r) * theta_stride + i];
         __syncthreads();
         RegTrellis<L> tr;
         tr.reset();
@@ -569,14 +569,15 @@ __global__ void __launch_bounds__(kTrainThreads, 1) detect_batched_kernel(const 
 }
 
 template <int L>
-static int launch_detect_batched(const float *theta, int R, const float *y, int T, int n_stages, float *decoded, float *priors,
-                                 cudaStream_t st) {
+static int launch_detect_batched(const float *theta, int shared_theta, int R, const float *y, int T, int n_stages, float *decoded,
+                                 float *priors, cudaStream_t st) {
     constexpr int S = 1 << L;
     constexpr int P = ThetaView<S>::P;
     const size_t smem = (size_t((P + 3) / 4 * 4) + size_t(kTrainThreads) * S) * sizeof(float);
     auto kern = detect_batched_kernel<L>;
     MVN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    kern<<<std::max(1, std::min(R, 2 * sm_count())), kTrainThreads, smem, st>>>(theta, R, y, T, n_stages, decoded, priors);
+    kern<<<std::max(1, std::min(R, 2 * sm_count())), kTrainThreads, smem, st>>>(theta, shared_theta ? 0 : P, R, y, T, n_stages, decoded,
+                                                                                priors);
     note_launch();
     MVN_CUDA(cudaGetLastError());
     return MVN_OK;
@@ -737,5 +738,16 @@ extern "C" int mvn_vnet_detect_batched(const float *theta, int R, int L, const f
     }
     if (R == 0 || T == 0) return MVN_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    MVN_TRAIN_DISPATCH(L, launch_detect_batched, theta, R, y, T, n_stages, decoded, priors_out, st)
+    MVN_TRAIN_DISPATCH(L, launch_detect_batched, theta, 0, R, y, T, n_stages, decoded, priors_out, st)
+}
+
+extern "C" int mvn_vnet_detect_small(const float *theta, int64_t B, int L, const float *y, int T, int n_stages, float *decoded,
+                                     float *priors_out, void *stream) {
+    if (B < 0 || B > (1 << 20) || T < 0 || n_stages < 0 || n_stages > T || (B > 0 && T > 0 && (!theta || !y || !decoded))) {
+        set_error("mvn_vnet_detect_small: bad argument (n_stages must be 0..T)");
+        return MVN_ERR_ARG;
+    }
+    if (B == 0 || T == 0) return MVN_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MVN_TRAIN_DISPATCH(L, launch_detect_batched, theta, 1, int(B), y, T, n_stages, decoded, priors_out, st)
 }

@@ -23,11 +23,29 @@ HIDDEN2_SIZE = 50
 SMALL_BATCH_FRAMES = 2048
 
 
+_packed_cache = {}
+
+
+def _packed(weights):
+    """[P] packed copy of the six weight tensors, re-packed only when one of them changed (tensor identity + version)."""
+    key = tuple((w.data_ptr(), w._version) for w in weights)
+    hit = _packed_cache.get('k')
+    if hit is None or hit[0] != key:
+        from .train import pack_params
+        hit = (key, pack_params(weights))
+        _packed_cache['k'] = hit
+    return hit[1]
+
+
 def _decode_vnet(y, weights, n_stages):
     if n_stages > y.shape[1]:
         raise IndexError(f'index {y.shape[1]} is out of bounds for dimension 1 with size {y.shape[1]}')
     if y.shape[0] >= SMALL_BATCH_FRAMES:
         return ops.vnet_decode(y, weights, n_stages)
+    L = int(weights[5].numel()).bit_length() - 1
+    if L <= 5:       # one launch: a CTA per word, priors symbol-parallel into shared memory, then the stage loop
+        from .train import detect_small
+        return detect_small(y, _packed(weights), L, n_stages)
     priors = ops.vnet_priors(y, weights)
     return ops.acs_decode(-priors, n_stages)
 

@@ -32,6 +32,7 @@ _PROTOS = {
     'mvn_vnet_priors_backward': (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'mvn_vnet_priors_backward2': (c_int, [c_void_p, c_int64, c_int] + [c_void_p] * 7),
     'mvn_vnet_detect_batched': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'mvn_vnet_detect_small': (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
 }
 _lib._PROTOS.update(_PROTOS)
 if _lib._lib is not None:          # library already loaded: bind the extra prototypes now
@@ -59,6 +60,16 @@ def unpack_params(theta: torch.Tensor, n_states: int):
         out.append(theta[..., o:o + n].reshape(theta.shape[:-1] + s))
         o += n
     return out
+
+
+def detect_small(y, theta, memory_length, n_stages=None):
+    """Single-launch VNETDetector.forward(y, 'val') for small batches: y [B,T], theta [P] packed weights."""
+    y = dev_f32(y)
+    B, T = y.shape
+    n = T if n_stages is None else int(n_stages)
+    dec = torch.empty((B, T), dtype=torch.float32, device=y.device)
+    check(load().mvn_vnet_detect_small(ptr(theta), B, int(memory_length), ptr(y), T, n, ptr(dec), None, stream()))
+    return dec
 
 
 def state_labels(memory_length: int, tx: torch.Tensor) -> torch.Tensor:
