@@ -419,8 +419,8 @@ def main():
     achieved_tflops = FLOP_PER_SYMBOL * sym_per_launch / (k_ms * 1e-3) / 1e12
     peak_tflops = 2 * peak_fma / 1e12
     traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get('vnet_decode_bytes_per_launch')
+    try:   # DRAM bytes per launch from the ncu --set full capture (profiles/traffic.json holds bytes per frame)
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get('vnet_decode_bytes_per_frame') * my_frames / n_launch
     except Exception:
         pass
     # The default kernel runs layers 2 and 3 (98 % of the flops) on the tensor cores: fp16 tcgen05 MMAs on a two-piece
