@@ -359,14 +359,14 @@ __global__ void __launch_bounds__(NT, (L <= 5) ? (MLSE ? 2 : 4) : 1) va_decode_k
     constexpr bool SP_REGS = (S <= 32);
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float *tile = smem + warp * (2 * kTileFloats);
-    float *ttile = tile + kTileFloats;
+    float *tile = smem + warp * kTileFloats;
+    float *ttile = tile;   // the target tile of a block is staged after its y tile has been consumed
     const float *row = tile + lane * kTileLd;
 
     constexpr bool PACKED = (L >= 2 && L <= 5);
     using Tr = typename std::conditional<PACKED, PackedTrellis<PACKED ? L : 2>, TrellisFor<L>>::type;
     Tr tr;
-    float *after_tiles = smem + WARPS * 2 * kTileFloats;
+    float *after_tiles = smem + WARPS * kTileFloats;
     if constexpr (L > kRegTrellisMaxL) {
         tr.init(after_tiles, NT, threadIdx.x);
         after_tiles += SmemTrellis<L>::bytes(NT) / sizeof(float);
@@ -535,7 +535,7 @@ static int launch_va_mode(VaParams p, cudaStream_t st) {
     // MLSE at 128 / 256 states: the survivor masks (T x S/2 bits per frame) share the CTA's shared memory with the
     // path metrics, so fewer frames are resident per CTA
     constexpr int NT = (L <= 5) ? 256 : (MLSE && L == 7) ? 64 : (MLSE && L == 8) ? 32 : 128;
-    size_t smem = size_t(NT / 32) * 2 * kTileFloats * sizeof(float);
+    size_t smem = size_t(NT / 32) * kTileFloats * sizeof(float);
     if (L > kRegTrellisMaxL) smem += SmemTrellis<L>::bytes(NT);
     if (MLSE) {
         p.surv_words = SurvStore<L>::words(p.n_stages);

@@ -249,7 +249,9 @@ __device__ __forceinline__ float pass(const Smem<S> &sm, const float *__restrict
                     const float b = W[LY::b2 + t.r[i]];
                     float4 h, r;
                     const float a0 = acc[i][0] + b, a1 = acc[i][1] + b, a2 = acc[i][2] + b, a3 = acc[i][3] + b;
-                    h.x = fmaxf(a0, 0.f), h.y = fmaxf(a1, 0.f), h.z = fmaxf(a2, 0.f), h.w = fmaxf(a3, 0.f);
+                    // (a < 0 ? 0 : a) instead of fmaxf: a NaN sample must reach the loss like torch's relu lets it, so that
+                    // run_train_loop's NaN rule can fire (fmaxf would return 0 for NaN)
+                    h.x = a0 < 0.f ? 0.f : a0, h.y = a1 < 0.f ? 0.f : a1, h.z = a2 < 0.f ? 0.f : a2, h.w = a3 < 0.f ? 0.f : a3;
                     *reinterpret_cast<float4 *>(sm.H2T + t.r[i] * ldn + t.c[0]) = h;
                     if (TAN) {
                         const float c = V[LY::b2 + t.r[i]];

@@ -232,3 +232,25 @@ def test_batched_detection_with_per_realisation_weights(mvn, L, T, n_stages):
 def test_training_rejects_unsupported_trellis(mvn):
     with pytest.raises(mvn.MVNError):
         mvn.BatchedVNetTrainer(torch.zeros(1, mvn.train.param_count(7)).cuda(), 7)
+
+
+def test_nan_loss_skips_the_update_like_run_train_loop(mvn):
+    """run_train_loop returns before backward / optimizer.step when the loss is NaN (trainer.py:495-498): a run whose word
+    holds a NaN sample keeps its weights and Adam state (and reports NaN), the other runs of the batch step normally."""
+    rng = np.random.RandomState(2)
+    w = [rng.randn(100, 1) * .7, rng.randn(100) * .5, rng.randn(50, 100) * .15, rng.randn(50) * .1,
+         rng.randn(16, 50) * .3, rng.randn(16) * .1]
+    theta0 = np.stack([pack(w)] * 3)
+    tr = mvn.BatchedVNetTrainer(cu(theta0), 4, lr=1e-3)
+    y = (rng.randn(3, 136) * 1.5).astype(np.float32)
+    tx = rng.randint(0, 2, (3, 136)).astype(np.float32)
+    tr.train_step(cu(y), cu(tx))                      # one clean step for every run
+    before = [t.clone() for t in (tr.theta, tr.adam_m, tr.adam_v, tr.adam_step)]
+    y[1, 17] = np.nan
+    loss = tr.train_step(cu(y), cu(tx)).cpu().numpy()
+    assert np.isnan(loss[1]) and np.isfinite(loss[0]) and np.isfinite(loss[2])
+    for now, was in zip((tr.theta, tr.adam_m, tr.adam_v, tr.adam_step), before):
+        assert torch.equal(now[1], was[1])            # untouched
+        assert not torch.equal(now[0], was[0]) and not torch.equal(now[2], was[2])
+    assert tr.adam_step.tolist() == [2, 1, 2]
+    assert torch.isfinite(tr.theta).all()
