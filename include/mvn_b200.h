@@ -82,6 +82,17 @@ int mvn_acs_block(const float *in_prob, const float *llrs, int llrs_stride, int6
 int mvn_acs_decode(const float *cost, int64_t B, int T, int L, int n_stages, int out_format,
                    void *decoded, float *final_pm, uint32_t *survivors, void *stream);
 
+/* Same with the thread layout selectable (for measurements; AUTO is what mvn_acs_decode uses):
+ * LANE_PER_FRAME  a lane owns a frame, metrics in registers (<= 64 states) / shared memory, no cross-lane traffic;
+ * STATES_ON_LANES the distinct metrics of a frame sit on S/2 lanes (4..64 states, 32/(S/2) frames per warp) or S/64 per
+ *                 lane (128 / 256 states, one frame per warp), butterflies and decision with warp shuffles / REDUX.
+ * AUTO = lane per frame up to 64 states, states on lanes at 128 / 256.  The survivor export always runs lane-per-frame. */
+#define MVN_LAYOUT_AUTO 0
+#define MVN_LAYOUT_LANE_PER_FRAME 1
+#define MVN_LAYOUT_STATES_ON_LANES 2
+int mvn_acs_decode_ex(const float *cost, int64_t B, int T, int L, int n_stages, int out_format, void *decoded,
+                      float *final_pm, uint32_t *survivors, int layout, void *stream);
+
 /* ---- a5+a3 fused: classical Viterbi with full CSI.  Replaces VADetector.forward
  * (va_detector.py:52-98) given the host-built table of va_detector.py:42-50.
  * y [B,T]; state_priors [n_h,S] fp32 (row k = noiseless outputs of tap block k; NOTE this is

@@ -29,6 +29,7 @@ _PROTOS = {
     'mvn_device_info': (c_int, [POINTER(c_int)] * 4),
     'mvn_acs_block': (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     'mvn_acs_decode': (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'mvn_acs_decode_ex': (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     'mvn_va_decode': (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p,
                               c_int, c_int, c_void_p, c_void_p]),
     'mvn_vnet_priors': (c_int, [c_void_p, c_int64, c_int] + [c_void_p] * 6 + [c_void_p, c_void_p]),

@@ -31,6 +31,7 @@ __global__ void acs_block_kernel(const float *__restrict__ in_prob, const float 
 // One lane per frame; the warp stages [32 frames x 32 floats] tiles of the [B, T*S] matrix.
 // =====================================================================================
 struct AcsParams {
+    int layout;   // MVN_LAYOUT_*
     const float *cost;
     int64_t B;
     int T, n_stages;
@@ -324,6 +325,80 @@ __global__ void __launch_bounds__(256) acs_decode_warp_kernel(AcsParams p) {
     }
 }
 
+// States on lanes for the SMALL trellises (4..32 states) — the layout BASELINE.json's north star sketches ("the 16 states
+// mapped to lanes, ACS butterflies with __shfl_sync").  G = S/2 lanes carry the distinct metrics of one frame (one each),
+// a warp holds 32/G frames.  Built for the A/B against lane-per-frame; mvn_acs_decode_ex selects it.
+template <int L>
+__global__ void __launch_bounds__(256) acs_decode_group_kernel(AcsParams p) {
+    static_assert(L >= 2 && L <= 5, "group layout: 4..32 states");
+    constexpr int S = 1 << L, G = S / 2, FPW = 32 / G;   // lanes per frame, frames per warp
+    const int lane = threadIdx.x & 31, sub = lane / G, j = lane % G, base = sub * G;
+    const unsigned gmask = (G == 32) ? kFull : (((1u << G) - 1u) << base);
+    const int64_t warp_global = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+    const int n_words = (p.T + 31) / 32;
+    const bool lower = j < G / 2;
+    const int src = base + (lower ? 2 * j : 2 * (j - G / 2));
+    for (int64_t f0 = warp_global * FPW; f0 < p.B; f0 += n_warps * FPW) {
+        const int64_t b = f0 + sub;
+        const bool live = b < p.B;
+        const float *cost = p.cost + (live ? b : 0) * int64_t(p.T) * S;
+        float pm = 0.f;
+        uint32_t bits = 0;
+        constexpr int U = 4;
+        float clo[U], chi[U];
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (u < p.n_stages) {
+                clo[u] = ldg_stream1(cost + int64_t(u) * S + j);
+                chi[u] = ldg_stream1(cost + int64_t(u) * S + G + j);
+            }
+        for (int t0 = 0; t0 < p.n_stages; t0 += U) {
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int t = t0 + u;
+                if (t < p.n_stages) {
+                    const uint32_t k = order_key(pm);
+                    const uint32_t m = __reduce_min_sync(gmask, k);
+                    const uint32_t who = __ballot_sync(kFull, k == m) & gmask;
+                    bits |= uint32_t((__ffs(who) - 1 - base) & 1) << (t & 31);   // lowest state attaining the minimum, & 1
+                    const float tl = pm + clo[u], th = pm + chi[u];
+                    const float a = fminf(__shfl_sync(kFull, tl, src), __shfl_sync(kFull, tl, src + 1));
+                    const float c = fminf(__shfl_sync(kFull, th, src), __shfl_sync(kFull, th, src + 1));
+                    pm = lower ? a : c;
+                    if (t + U < p.n_stages) {
+                        clo[u] = ldg_stream1(cost + int64_t(t + U) * S + j);
+                        chi[u] = ldg_stream1(cost + int64_t(t + U) * S + G + j);
+                    }
+                    if ((t & 31) == 31 || t == p.n_stages - 1) {
+                        if (p.decoded && live) {
+                            if (p.out_format == MVN_OUT_F32) {
+                                for (int col = (t & ~31) + j; col < min(p.T, (t & ~31) + 32); col += G)
+                                    static_cast<float *>(p.decoded)[b * p.T + col] = float((bits >> (col & 31)) & 1u);
+                            } else if (j == 0) {
+                                static_cast<uint32_t *>(p.decoded)[b * n_words + (t >> 5)] = bits;
+                            }
+                        }
+                        bits = 0;
+                    }
+                }
+            }
+        }
+        if (p.decoded && live)
+            for (int t0 = ((p.n_stages + 31) / 32) * 32; t0 < p.T; t0 += 32) {
+                if (p.out_format == MVN_OUT_F32) {
+                    for (int col = t0 + j; col < min(p.T, t0 + 32); col += G) static_cast<float *>(p.decoded)[b * p.T + col] = 0.f;
+                } else if (j == 0) {
+                    static_cast<uint32_t *>(p.decoded)[b * n_words + t0 / 32] = 0u;
+                }
+            }
+        if (p.final_pm && live) {
+            p.final_pm[b * S + j] = pm;
+            p.final_pm[b * S + G + j] = pm;
+        }
+    }
+}
+
 // =====================================================================================
 // a5+a3 fused: y[B,T] + state_priors[n_h,S] -> bits.  cost = (y-sp)^2/2 - ln sqrt(2 pi) in
 // separately rounded fp32 ops (no contraction of d*d into the following op: the halving is exact,
@@ -499,10 +574,25 @@ __global__ void __launch_bounds__(NT, (L <= 5) ? (MLSE ? 2 : 4) : 1) va_decode_k
 // =====================================================================================
 template <int L>
 static int launch_acs(const AcsParams &p, cudaStream_t st) {
-    if constexpr (L >= 7) {   // (at 64 states the lane-per-frame kernel with its register trellis is faster: 63 % vs 39 % of HBM)
-        // states on lanes (one warp per frame) unless the survivor export is wanted (that stays with the lane-per-frame
-        // kernel, which assembles the bit masks per lane); needs 16-byte aligned rows for the vector loads at 256 states
-        if (!p.survivors && (reinterpret_cast<uintptr_t>(p.cost) & 15u) == 0) {
+    if constexpr (L >= 2 && L <= 5) {
+        if (p.layout == MVN_LAYOUT_STATES_ON_LANES && !p.survivors) {   // only on request: lane-per-frame is faster here
+            auto kern = acs_decode_group_kernel<L>;
+            int per_sm = 1;
+            MVN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
+            const int64_t fpw = 32 / ((1 << L) / 2);
+            const int grid = int(std::min<int64_t>((p.B + 8 * fpw - 1) / (8 * fpw), int64_t(sm_count()) * std::max(per_sm, 1)));
+            kern<<<grid, 256, 0, st>>>(p);
+            note_launch();
+            MVN_CUDA(cudaGetLastError());
+            return MVN_OK;
+        }
+    }
+    if constexpr (L >= 6) {
+        // states on lanes (one warp per frame): the default at 128 / 256 states (at 64 the lane-per-frame kernel with its
+        // register trellis is faster: 65 % vs 39 % of HBM), unless the survivor export is wanted (that stays with the
+        // lane-per-frame kernel, which assembles the bit masks per lane); needs 16-byte aligned rows for the vector loads
+        const bool want = p.layout == MVN_LAYOUT_STATES_ON_LANES || (p.layout == MVN_LAYOUT_AUTO && L >= 7);
+        if (want && !p.survivors && (reinterpret_cast<uintptr_t>(p.cost) & 15u) == 0) {
             auto kern = acs_decode_warp_kernel<L>;
             int per_sm = 1;
             MVN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
@@ -605,20 +695,25 @@ extern "C" int mvn_acs_block(const float *in_prob, const float *llrs, int llrs_s
     return MVN_OK;
 }
 
-extern "C" int mvn_acs_decode(const float *cost, int64_t B, int T, int L, int n_stages, int out_format,
-                              void *decoded, float *final_pm, uint32_t *survivors, void *stream) {
+extern "C" int mvn_acs_decode_ex(const float *cost, int64_t B, int T, int L, int n_stages, int out_format, void *decoded,
+                                 float *final_pm, uint32_t *survivors, int layout, void *stream) {
     if (L < 1 || L > 8) {
         set_error("memory_length %d outside [1,8]", L);
         return MVN_ERR_ARG;
     }
     if (B < 0 || T < 0 || n_stages < 0 || n_stages > T || (B > 0 && T > 0 && !cost) ||
-        (out_format != MVN_OUT_F32 && out_format != MVN_OUT_BITS)) {
-        set_error("mvn_acs_decode: bad argument (B=%lld T=%d n_stages=%d)", (long long)B, T, n_stages);
+        (out_format != MVN_OUT_F32 && out_format != MVN_OUT_BITS) || layout < MVN_LAYOUT_AUTO || layout > MVN_LAYOUT_STATES_ON_LANES) {
+        set_error("mvn_acs_decode: bad argument (B=%lld T=%d n_stages=%d layout=%d)", (long long)B, T, n_stages, layout);
         return MVN_ERR_ARG;
     }
     if (B == 0 || T == 0) return MVN_OK;
-    AcsParams p{cost, B, T, n_stages, out_format, decoded, final_pm, survivors, (B + 31) / 32};
+    AcsParams p{layout, cost, B, T, n_stages, out_format, decoded, final_pm, survivors, (B + 31) / 32};
     return acs_decode_impl(p, L, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mvn_acs_decode(const float *cost, int64_t B, int T, int L, int n_stages, int out_format,
+                              void *decoded, float *final_pm, uint32_t *survivors, void *stream) {
+    return mvn_acs_decode_ex(cost, B, T, L, n_stages, out_format, decoded, final_pm, survivors, MVN_LAYOUT_AUTO, stream);
 }
 
 extern "C" int mvn_va_decode_ex(const float *y, int64_t B, int T, int L, int n_stages, const float *state_priors,

@@ -67,8 +67,12 @@ def acs_block(in_prob, llrs, n_states):
     return out, idx
 
 
-def acs_decode(cost, n_stages=None, out_format=OUT_F32, return_final_pm=False, return_survivors=False):
-    """Stage loop on cost [B,T,S] (the a3 loop).  Returns decoded (+ final_pm, + survivors)."""
+ACS_LAYOUTS = {'auto': 0, 'lane_per_frame': 1, 'states_on_lanes': 2}                          # MVN_LAYOUT_*
+
+
+def acs_decode(cost, n_stages=None, out_format=OUT_F32, return_final_pm=False, return_survivors=False, layout='auto'):
+    """Stage loop on cost [B,T,S] (the a3 loop).  Returns decoded (+ final_pm, + survivors).  layout: thread layout of
+    the kernel (ACS_LAYOUTS; 'auto' = lane per frame up to 64 states, states on lanes at 128 / 256)."""
     cost = dev_f32(cost)
     B, T, S = cost.shape
     L = _mem_len(S)
@@ -77,7 +81,7 @@ def acs_decode(cost, n_stages=None, out_format=OUT_F32, return_final_pm=False, r
     pm = torch.empty((B, S), dtype=torch.float32, device=cost.device) if return_final_pm else None
     sw = max(1, S // 64)
     surv = torch.zeros((B, n, sw), dtype=torch.int32, device=cost.device) if return_survivors else None
-    check(load().mvn_acs_decode(ptr(cost), B, T, L, n, out_format, ptr(dec), ptr(pm), ptr(surv), stream()))
+    check(load().mvn_acs_decode_ex(ptr(cost), B, T, L, n, out_format, ptr(dec), ptr(pm), ptr(surv), ACS_LAYOUTS[layout], stream()))
     res = (dec,)
     if return_final_pm:
         res += (pm,)

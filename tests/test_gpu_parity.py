@@ -101,12 +101,12 @@ def test_acs_block_matches(mvn, L):
     assert np.array_equal(val1.cpu().numpy(), orc.acs_stage(pm, np.broadcast_to(c[:, :1], pm.shape))[0])
 
 
-@pytest.mark.parametrize('L', [6, 7, 8])
+@pytest.mark.parametrize('L', [2, 3, 4, 5, 6, 7, 8])
 def test_acs_decode_states_on_lanes(mvn, L):
-    """128 / 256 states run one warp per frame with the states on the lanes (registers + shuffles, costs straight from
-    HBM); without the survivor export that is the kernel mvn_acs_decode launches: bits and final metrics bit-exact vs the
-    oracle, random and exact-tie costs, ragged loop lengths, both output formats; and identical to the lane-per-frame
-    kernel (which the survivor export selects)."""
+    """The states-on-lanes layout (S/2 lanes per frame for 4..64 states, one warp per frame with S/64 metrics per lane at
+    128 / 256 states; butterflies by shuffles, decision by REDUX.MIN + ballot): bits and final metrics bit-exact vs the
+    oracle — random and exact-tie costs, +-0, ragged loop lengths, both output formats — and identical to the
+    lane-per-frame kernel.  'auto' picks it at 128 / 256 states."""
     rng = np.random.RandomState(300 + L)
     S, B, T = 2 ** L, 77, 45
     cost = (rng.randn(B, T, S) * 2).astype(np.float32)
@@ -115,14 +115,12 @@ def test_acs_decode_states_on_lanes(mvn, L):
     cost[2] = -0.0
     for n in (T, T - 13, 32, 1, 0):
         ref, pm_ref = orc.acs_decode(cost, n)
-        dec, pm = mvn.ops.acs_decode(cu(cost), n, return_final_pm=True)
-        assert np.array_equal(dec.cpu().numpy(), ref), (L, n)
-        assert np.array_equal(pm.cpu().numpy(), pm_ref), (L, n)
-        words = mvn.ops.acs_decode(cu(cost), n, out_format=mvn.OUT_BITS)
-        assert np.array_equal(mvn.ops.unpack_bits(words, T).cpu().numpy(), ref)
-        if n > 0:
-            dec2, _, _ = mvn.ops.acs_decode(cu(cost), n, return_final_pm=True, return_survivors=True)
-            assert torch.equal(dec2, dec)
+        for layout in ('states_on_lanes', 'lane_per_frame', 'auto'):
+            dec, pm = mvn.ops.acs_decode(cu(cost), n, return_final_pm=True, layout=layout)
+            assert np.array_equal(dec.cpu().numpy(), ref), (L, n, layout)
+            assert np.array_equal(pm.cpu().numpy(), pm_ref), (L, n, layout)
+            words = mvn.ops.acs_decode(cu(cost), n, out_format=mvn.OUT_BITS, layout=layout)
+            assert np.array_equal(mvn.ops.unpack_bits(words, T).cpu().numpy(), ref)
 
 
 # ------------------------------------------------------------------------------- a4/a5 VA
