@@ -570,6 +570,91 @@ __global__ void __launch_bounds__(NT, (L <= 5) ? (MLSE ? 2 : 4) : 1) va_decode_k
 }
 
 // =====================================================================================
+// a5+a3 for 128 / 256 states, STATES ON LANES (see acs_decode_warp_kernel): one warp per frame, lane l owns the metrics
+// pm[R l .. R l + R) and the 2R noiseless outputs sp[R l + i], sp[S/2 + R l + i] of its sources; y comes in as one
+// coalesced 32-sample load per 32 stages and is broadcast by shuffle.  Branch metrics with the reference's three
+// separately rounded operations.  Reference rule only (the fused traceback stays with the lane-per-frame kernel).
+// =====================================================================================
+template <int L>
+__global__ void __launch_bounds__(256) va_decode_warp_kernel(VaParams p) {
+    static_assert(L >= 7 && L <= 8, "states-on-lanes VA: 128 / 256 states");
+    constexpr int S = 1 << L, H = S / 2, R = H / 32;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+    const int n_words = (p.T + 31) / 32;
+    const bool lower = lane < 16;
+    const int src = lower ? 2 * lane : 2 * (lane - 16);
+    unsigned bit_errs = 0, frame_errs = 0, frames = 0;
+    for (int64_t b = warp_global; b < p.B; b += n_warps) {
+        const float *sp_row = p.sp + int64_t(b % p.n_h) * S;
+        float slo[R], shi[R], pm[R];
+#pragma unroll
+        for (int i = 0; i < R; i++) {
+            slo[i] = __ldg(sp_row + R * lane + i);
+            shi[i] = __ldg(sp_row + H + R * lane + i);
+            pm[i] = 0.f;
+        }
+        unsigned frame_bit_errs = 0;
+        for (int t0 = 0; t0 < p.T; t0 += 32) {
+            uint32_t bits = 0;
+            const int t_end = min(32, p.n_stages - t0);
+            const float ytile = (t_end > 0 && t0 + lane < p.T) ? ldg_stream1(p.y + b * p.T + t0 + lane) : 0.f;
+            for (int tt = 0; tt < t_end; tt++) {
+                const float yv = __shfl_sync(kFull, ytile, tt);
+                uint32_t kmin = order_key(pm[0]), par = 0u;
+#pragma unroll
+                for (int i = 1; i < R; i++) {
+                    const uint32_t k = order_key(pm[i]);
+                    if (k < kmin) {
+                        kmin = k;
+                        par = uint32_t(i & 1);
+                    }
+                }
+                const uint32_t m = __reduce_min_sync(kFull, kmin);
+                const uint32_t who = __ballot_sync(kFull, kmin == m);
+                bits |= __shfl_sync(kFull, par, __ffs(who) - 1) << tt;
+                float nlo[R / 2], nhi[R / 2];
+#pragma unroll
+                for (int k = 0; k < R / 2; k++) {
+                    nlo[k] = fminf(pm[2 * k] + va_cost(yv, slo[2 * k]), pm[2 * k + 1] + va_cost(yv, slo[2 * k + 1]));
+                    nhi[k] = fminf(pm[2 * k] + va_cost(yv, shi[2 * k]), pm[2 * k + 1] + va_cost(yv, shi[2 * k + 1]));
+                }
+#pragma unroll
+                for (int i = 0; i < R; i++) {
+                    const float a = __shfl_sync(kFull, nlo[i % (R / 2)], src + i / (R / 2));
+                    const float c = __shfl_sync(kFull, nhi[i % (R / 2)], src + i / (R / 2));
+                    pm[i] = lower ? a : c;
+                }
+            }
+            if (p.decoded) {
+                if (p.out_format == MVN_OUT_F32) {
+                    if (t0 + lane < p.T) static_cast<float *>(p.decoded)[b * p.T + t0 + lane] = float((bits >> lane) & 1u);
+                } else if (lane == 0) {
+                    static_cast<uint32_t *>(p.decoded)[b * n_words + t0 / 32] = bits;
+                }
+            }
+            if (p.target && t0 < p.target_T) {
+                const bool in = t0 + lane < p.target_T;
+                const int tgt = in ? int(ldg_stream1(p.target + b * p.target_T + t0 + lane)) : 0;
+                frame_bit_errs += __popc(__ballot_sync(kFull, in && tgt != int((bits >> lane) & 1u)));
+            }
+        }
+        if (p.target && !(p.pilot_period > 0 && b % p.pilot_period == 0)) {
+            bit_errs += frame_bit_errs;
+            frame_errs += frame_bit_errs ? 1u : 0u;
+            frames += 1u;
+        }
+    }
+    if (p.target && lane == 0 && frames) {
+        atomicAdd(p.counters + MVN_CNT_BIT_ERRORS, (unsigned long long)bit_errs);
+        atomicAdd(p.counters + MVN_CNT_FRAME_ERRORS, (unsigned long long)frame_errs);
+        atomicAdd(p.counters + MVN_CNT_BITS, (unsigned long long)frames * unsigned(p.target_T));
+        atomicAdd(p.counters + MVN_CNT_FRAMES, (unsigned long long)frames);
+    }
+}
+
+// =====================================================================================
 // host wrappers
 // =====================================================================================
 template <int L>
@@ -651,6 +736,18 @@ static int launch_va_mode(VaParams p, cudaStream_t st) {
 
 template <int L>
 static int launch_va(const VaParams &p, cudaStream_t st) {
+    if constexpr (L >= 7) {
+        if (p.decision == MVN_DECIDE_REFERENCE) {   // 128 / 256 states: one warp per frame, states on lanes
+            auto kern = va_decode_warp_kernel<L>;
+            int per_sm = 1;
+            MVN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
+            const int grid = int(std::min<int64_t>((p.B + 7) / 8, int64_t(sm_count()) * std::max(per_sm, 1)));
+            kern<<<grid, 256, 0, st>>>(p);
+            note_launch();
+            MVN_CUDA(cudaGetLastError());
+            return MVN_OK;
+        }
+    }
     return p.decision == MVN_DECIDE_REFERENCE ? launch_va_mode<L, false>(p, st) : launch_va_mode<L, true>(p, st);
 }
 

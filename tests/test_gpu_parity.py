@@ -187,6 +187,31 @@ def test_va_detector_class_matches_reference_run(mvn):
         bad(torch.zeros(4, 8).cuda(), 'val', 10.0, 0.2)
 
 
+@pytest.mark.parametrize('L', [7, 8])
+def test_va_states_on_lanes_counters(mvn, L):
+    """128 / 256 states: the one-warp-per-frame VA kernel — bits bit-exact vs the oracle with several tap blocks, ragged
+    loop length, bit-packed output, and the fused BER / FER counters with pilots and a target narrower than y."""
+    from meta_viterbinet_b200.channel_taps import state_priors_table
+    rng = np.random.RandomState(40 + L)
+    B, T, Tt = 90, 70, 61
+    h = (np.exp(-0.3 * np.arange(L)) * (1 + 0.1 * rng.randn(6, L))).astype(np.float64)     # 6 tap blocks, B % 6 == 0
+    bits = rng.randint(0, 2, size=(B, T))
+    y = orc.isi_awgn(bits, h[np.arange(B) % 6], 5.0, L, rng).astype(np.float32)
+    y[:4] = np.round(y[:4])
+    table = cu(state_priors_table(h, L))
+    for n in (T, T - 9, 33):
+        ref = orc.va_decode(y, h, L, n)
+        cnt = mvn.ops.new_counters()
+        tgt = bits[:, :Tt].astype(np.float32)
+        dec = mvn.ops.va_decode(cu(y), table, n, target=cu(tgt), pilot_period=4, counters=cnt).cpu().numpy()
+        assert np.array_equal(dec, ref), (L, n)
+        keep = np.arange(B) % 4 != 0
+        err = ref[keep][:, :Tt] != tgt[keep]
+        assert cnt.tolist() == [int(err.sum()), int(err.any(axis=1).sum()), int(keep.sum()) * Tt, int(keep.sum())]
+        words = mvn.ops.va_decode(cu(y), table, n, out_format=mvn.OUT_BITS)
+        assert np.array_equal(mvn.ops.unpack_bits(words, T).cpu().numpy(), ref)
+
+
 # ------------------------------------------------------------------------------- a6/a7 priors
 def _w(g, prefix):
     return [g[f'{prefix}{i}'] for i in range(6)]
