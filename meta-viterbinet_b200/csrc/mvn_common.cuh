@@ -220,11 +220,17 @@ struct SmemTrellis {
     }
     static __host__ __device__ constexpr size_t bytes(int ncols_) { return size_t(2) * H * ncols_ * sizeof(float); }
     __device__ __forceinline__ float &at(int buf, int h) const { return base[(size_t(buf) * H + h) * ncols]; }
+    // minima over the even / odd states of the current metrics (e, o) and of the metrics being built (ne, no): the
+    // decision needs only their order; an exact tie falls back to the ordered scan (lowest index wins)
+    float e, o, ne, no;
     __device__ __forceinline__ void reset() {
         for (int h = 0; h < H; h++) at(0, h) = 0.f;
         cur = 0;
+        e = o = 0.f;
+        ne = no = 3.0e38f;
     }
     __device__ __forceinline__ uint32_t decide() const {
+        if (o != e) return o < e ? 1u : 0u;
         float best = at(cur, 0);
         uint32_t bit = 0;
 #pragma unroll 8
@@ -242,12 +248,19 @@ struct SmemTrellis {
         for (int i = 0; i < C / 2; i++) {
             const float a = at(cur, (c * C + 2 * i) % H) + cost[2 * i];
             const float b = at(cur, (c * C + 2 * i + 1) % H) + cost[2 * i + 1];
-            at(cur ^ 1, c * (C / 2) + i) = fminf(a, b);
+            const float v = fminf(a, b);
+            at(cur ^ 1, c * (C / 2) + i) = v;
+            if (i & 1) no = fminf(no, v);   // new state c*(C/2)+i: C/2 is even for every trellis kept in shared memory
+            else ne = fminf(ne, v);
             surv |= uint32_t(b < a) << i;
         }
         return surv;
     }
-    __device__ __forceinline__ void commit() { cur ^= 1; }
+    __device__ __forceinline__ void commit() {
+        cur ^= 1;
+        e = ne, o = no;
+        ne = no = 3.0e38f;
+    }
     __device__ __forceinline__ float metric(int h) const { return at(cur, h); }
 };
 
