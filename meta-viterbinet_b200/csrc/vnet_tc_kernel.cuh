@@ -299,19 +299,27 @@ __device__ __forceinline__ void h2_to_tmem(uint32_t slot_lane) {
 
 template <int L, bool MLSE>
 __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch timeout_flag, long long *trace) {
-    static_assert(L <= 7, "tcgen05 variant: the priors of one stage must fit the slot's 128 D columns");
+    static_assert(L <= 8, "tcgen05 variant: memory_length 1..8");
     // L <= 6: priors_main | priors_corr side by side in the slot's two 64-column D regions (one N = 2 N2 MMA per k-step).
     // L == 7: 128 priors fill both regions, so the correction chain is computed first and folded into the main chain by
     //         the tensor core itself (scale-input-d: D = A B + D 2^-11): ONE 128-column accumulator.
-    constexpr bool MERGED = (L == 7);
+    // L == 8: 256 priors go through the same 128 columns in TWO layer-3 passes per stage (states 0..127, then 128..255:
+    //         the stage loop consumes the source states in that order anyway); the second pass is issued by a consumer
+    //         thread once all consumer warps have read the first half.  The 256-state path metrics of 128 frames (131 KB)
+    //         do not fit shared memory next to W3's fp16 pieces (64 KB), so a CTA tile is 64 frames: TMEM lane quadrants
+    //         0 and 1 work, the warps of quadrants 2 and 3 only keep the barrier protocol in step.
+    constexpr bool MERGED = (L >= 7);
+    constexpr int NPASS = (L == 8) ? 2 : 1;      // layer-3 passes per stage
+    constexpr int kQ = (L == 8) ? 2 : 4;         // active TMEM lane quadrants = 32-frame warp tiles per CTA tile
     using D = TrellisDims<L>;
     constexpr int S = D::S, C = D::C, NCH = D::NCH, NW = tc::kProdWarps + tc::kConvWarps + tc::kConsWarps;
     constexpr int N2 = tc::n2_of(S), kB2Bytes = tc::b2_bytes(S);
+    constexpr int N3 = N2 / NPASS;               // output columns of one layer-3 pass
     constexpr uint32_t kLBO2 = (2 * N2 / 8) * 128;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(8) uint64_t d_full[2], slot_free[2], a_full[2], d2_full[2];
-    constexpr int NT_TILES = tc::kProdWarps + tc::kConsWarps;                    // producers and consumers stage tiles
+    constexpr int NT_TILES = 4 * kQ;                                             // active producers (3 per quadrant) and consumers stage tiles
     uint8_t *sB = smem_raw;                                                      // W2 pieces, hi rows | lo rows
     float *tiles = reinterpret_cast<float *>(smem_raw + tc::kBBytes);            // one 32x32 tile per such warp
     float *sP = tiles + NT_TILES * kTileFloats;                                  // [56][4] pair table for the packed sigmoid
@@ -321,7 +329,8 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
     const bool converter = !producer && warp < tc::kProdWarps + tc::kConvWarps;
     const bool mma_warp = warp == NW;
     // tiles: one per producer warp (y) and one per consumer warp (targets); converters and the MMA warp use none
-    float *tile = tiles + (producer ? warp : tc::kProdWarps + quad) * kTileFloats;
+    const bool active = quad < kQ;
+    float *tile = tiles + (producer ? (warp >> 2) * kQ + (active ? quad : 0) : 3 * kQ + (active ? quad : 0)) * kTileFloats;
 
     // ---- W2 (and b2 as column k=100) -> fp16 hi / scaled-lo pieces in the canonical K-major layout
     for (int idx = tid; idx < tc::kN * tc::kK; idx += tc::kThreadsTc) {
@@ -375,7 +384,7 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
     const uint32_t lane_base = uint32_t(quad * 32) << 16;
     const uint32_t sB_addr = smem_addr(sB), sB2_addr = smem_addr(sB2);
     // D=F32, A=B=F16, both K-major, N>>3 at bit 17, M>>4 at bit 24; "w" = hi and lo pieces of B side by side
-    constexpr uint32_t idesc2 = (1u << 4) | (uint32_t(N2 >> 3) << 17) | (uint32_t(tc::kM >> 4) << 24);
+    constexpr uint32_t idesc2 = (1u << 4) | (uint32_t(N3 >> 3) << 17) | (uint32_t(tc::kM >> 4) << 24);
     constexpr uint32_t idesc2w = (1u << 4) | (uint32_t(2 * N2 >> 3) << 17) | (uint32_t(tc::kM >> 4) << 24);
     constexpr uint32_t idesc = (1u << 4) | (uint32_t(tc::kN >> 3) << 17) | (uint32_t(tc::kM >> 4) << 24);
     constexpr uint32_t idescw = (1u << 4) | (uint32_t(2 * tc::kN >> 3) << 17) | (uint32_t(tc::kM >> 4) << 24);
@@ -384,16 +393,42 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
     const bool vec_out = p.out_format == MVN_OUT_F32 && is_vec_ok(p.decoded, p.T, p.T);
     const bool vec_tgt = p.target && is_vec_ok(p.target, p.target_T, p.target_T);
     const int n_words = (p.T + 31) / 32;
-    const int64_t n_cta_tiles = (p.n_warp_tiles + 3) / 4;  // CTA tile = 4 warp tiles of 32 frames
+    const int64_t n_cta_tiles = (p.n_warp_tiles + kQ - 1) / kQ;  // CTA tile = kQ warp tiles of 32 frames
     uint32_t n = 0;                                        // running stage counter: slot = n & 1, use = n >> 1
+    // layer 3 with the correction chain folded in by scale-input-d (MERGED): pass `half` covers states [N3 half, N3 half + N3)
+    auto issue_layer3_merged = [&](uint32_t ts, int half) {
+        constexpr uint32_t kLoRows = (N2 / 8) * 128;       // byte offset of the W3_lo rows inside a k-chunk
+        const uint32_t rows = uint32_t(half) * (N3 / 8) * 128;
+#pragma unroll
+        for (int j = 0; j < tc::kK2Steps; j++)   // corr = h2_hi W3_lo
+            tc::mma_f16_ts(ts + tc::oDm, ts + tc::oAh + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2 + kLoRows + rows, kLBO2),
+                           idesc2, j > 0);
+#pragma unroll
+        for (int j = 0; j < tc::kK2Steps; j++)   // corr += h2_lo W3_hi
+            tc::mma_f16_ts(ts + tc::oDm, ts + tc::oAl + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2 + rows, kLBO2), idesc2, 1);
+        // priors = h2_hi W3_hi + corr / 2048: the first MMA of the main chain reads D scaled by 2^-11
+        tc::mma_f16_ts_scale11(ts + tc::oDm, ts + tc::oAh, tc::b_desc(sB2_addr + rows, kLBO2), idesc2);
+#pragma unroll
+        for (int j = 1; j < tc::kK2Steps; j++)
+            tc::mma_f16_ts(ts + tc::oDm, ts + tc::oAh + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2 + rows, kLBO2), idesc2, 1);
+    };
 
     if (producer) {
         int rot = 0;  // which of the quadrant's three warps takes the seventh k-step in this stage
         for (int64_t ct = blockIdx.x; ct < n_cta_tiles; ct += gridDim.x) {
-            const int64_t row0 = (ct * 4 + quad) * 32;
+            const int64_t row0 = (ct * kQ + quad) * 32;
             for (int t0 = 0; t0 < p.T; t0 += 32) {
                 const int t_end = min(32, p.n_stages - t0);
                 if (t_end <= 0) continue;
+                if (!active) {   // (L == 8) this quadrant carries no frames: keep a_full's arrival count in step
+                    for (int tt = 0; tt < t_end; tt++, n++) {
+                        tc::mbar_wait<true>(smem_addr(&slot_free[n & 1]), ((n >> 1) & 1) ^ 1, timeout_flag);
+                        __syncwarp();
+                        if (lane == 0) tc::mbar_arrive(smem_addr(&a_full[n & 1]));
+                        __syncwarp();
+                    }
+                    continue;
+                }
                 warp_load_tile(p.y, p.B, p.T, p.T, row0, t0, tile, lane, vec_in);
 #pragma unroll 1
                 for (int tt = 0; tt < t_end; tt++, n++) {
@@ -483,7 +518,7 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
                     tc::mbar_wait<MVN_CONS_PARK>(smem_addr(&d_full[slot]), use & 1, timeout_flag);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     TC_TRACE(7, warp == tc::kProdWarps && lane == 0);
-                    tc::h2_to_tmem(slot_lane);
+                    if (active) tc::h2_to_tmem(slot_lane);
                     asm volatile("tcgen05.fence::before_thread_sync;");
                     TC_TRACE(8, warp == tc::kProdWarps && lane == 0);
                     asm volatile("bar.sync 2, %0;" ::"n"(32 * tc::kConvWarps));
@@ -499,22 +534,8 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
                             for (int j = 0; j < tc::kK2Steps; j++)   // priors_corr += h2_lo W3_hi
                                 tc::mma_f16_ts(ts + tc::oDm + N2, ts + tc::oAl + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2, kLBO2),
                                                idesc2, 1);
-                        } else {                   // 4 + 4 + 4 MMAs of N = 128 into one accumulator
-                            constexpr uint32_t kLoRows = (N2 / 8) * 128;   // byte offset of the W3_lo rows inside a k-chunk
-#pragma unroll
-                            for (int j = 0; j < tc::kK2Steps; j++)   // corr = h2_hi W3_lo
-                                tc::mma_f16_ts(ts + tc::oDm, ts + tc::oAh + j * 8,
-                                               tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2 + kLoRows, kLBO2), idesc2, j > 0);
-#pragma unroll
-                            for (int j = 0; j < tc::kK2Steps; j++)   // corr += h2_lo W3_hi
-                                tc::mma_f16_ts(ts + tc::oDm, ts + tc::oAl + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2, kLBO2),
-                                               idesc2, 1);
-                            // priors = h2_hi W3_hi + corr / 2048: the first MMA of the main chain reads D scaled by 2^-11
-                            tc::mma_f16_ts_scale11(ts + tc::oDm, ts + tc::oAh, tc::b_desc(sB2_addr, kLBO2), idesc2);
-#pragma unroll
-                            for (int j = 1; j < tc::kK2Steps; j++)
-                                tc::mma_f16_ts(ts + tc::oDm, ts + tc::oAh + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2, kLBO2),
-                                               idesc2, 1);
+                        } else {                   // 4 + 4 + 4 MMAs of N = 128 into one accumulator (pass 0: states 0..127)
+                            issue_layer3_merged(ts, 0);
                         }
                         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                             smem_addr(&d2_full[slot])));
@@ -531,18 +552,18 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
         // next tile by then, so the traceback overlaps their work).
         typename std::conditional<(L <= 5), RegTrellis<L>, SmemTrellis<L>>::type tr;
         float *after_w3 = reinterpret_cast<float *>(sB2 + kB2Bytes);
-        if constexpr (L > 5) {  // path metrics of the 128 frames of the tile: [2][H][128] floats behind the W3 pieces
-            tr.init(after_w3, 32 * tc::kConsWarps, quad * 32 + lane);
-            after_w3 += SmemTrellis<L>::bytes(32 * tc::kConsWarps) / sizeof(float);
+        if constexpr (L > 5) {  // path metrics of the frames of the tile: [2][H][32 kQ] floats behind the W3 pieces
+            tr.init(after_w3, 32 * kQ, (active ? quad : 0) * 32 + lane);
+            after_w3 += SmemTrellis<L>::bytes(32 * kQ) / sizeof(float);
         }
         SurvStore<L> surv;
         if constexpr (MLSE) surv.init(reinterpret_cast<uint32_t *>(after_w3) + size_t(quad) * p.surv_words * 32, lane);
         ErrAcc acc;
         constexpr int kConsFirst = tc::kProdWarps + tc::kConvWarps;
         for (int64_t ct = blockIdx.x; ct < n_cta_tiles; ct += gridDim.x) {
-            const int64_t row0 = (ct * 4 + quad) * 32;
+            const int64_t row0 = (ct * kQ + quad) * 32;
             const int64_t b = row0 + lane;
-            tr.reset();
+            if (active) tr.reset();
             unsigned frame_bit_errs = 0;
             auto emit = [&](int t0, uint32_t bits) {
                 if (p.decoded) {
@@ -564,8 +585,10 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
                 for (int tt = 0; tt < t_end; tt++, n++) {
                     const uint32_t slot = n & 1, use = n >> 1;
                     const uint32_t ts = tmem + slot * tc::kSlotCols, slot_lane = ts + lane_base;
-                    if constexpr (!MLSE) bits |= tr.decide() << tt;   // metrics entering this stage; overlaps the wait
-                    tc::mbar_wait<MVN_CONS_PARK>(smem_addr(&d2_full[slot]), use & 1, timeout_flag);
+                    if constexpr (!MLSE) {
+                        if (active) bits |= tr.decide() << tt;   // metrics entering this stage; overlaps the wait
+                    }
+                    tc::mbar_wait<MVN_CONS_PARK>(smem_addr(&d2_full[slot]), (NPASS * use) & 1, timeout_flag);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     TC_TRACE(11, warp == kConsFirst && lane == 0);
                     float *dst = (p.priors_out && b < p.B) ? p.priors_out + (b * p.T + t0 + tt) * S : nullptr;
@@ -574,16 +597,20 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
                     auto chunk = [&](auto cc) {
                         constexpr int c = decltype(cc)::value;
                         constexpr bool last = (c == NCH - 1);
+                        constexpr int col = 16 * (c % (NCH / NPASS));   // a pass refills the same D columns
                         float pm_[16], pc_[16];
-                        tc::tmem_ld16(slot_lane + tc::oDm + 16 * c, pm_);
-                        if constexpr (!MERGED) tc::tmem_ld16(slot_lane + tc::oDm + N2 + 16 * c, pc_);
-                        asm volatile("tcgen05.wait::ld.sync.aligned;");
+                        if (active) {
+                            tc::tmem_ld16(slot_lane + tc::oDm + col, pm_);
+                            if constexpr (!MERGED) tc::tmem_ld16(slot_lane + tc::oDm + N2 + col, pc_);
+                            asm volatile("tcgen05.wait::ld.sync.aligned;");
+                        }
                         if (last) {
                             asm volatile("tcgen05.fence::before_thread_sync;");
                             TC_TRACE(12, warp == kConsFirst && lane == 0);
                             __syncwarp();
                             if (lane == 0) tc::mbar_arrive(smem_addr(&slot_free[slot]));  // the slot's A and D columns may be refilled
                         }
+                        if (!active) return;
                         float pr[C], cost[C];
 #pragma unroll
                         for (int i = 0; i < C; i++) {
@@ -599,13 +626,31 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
                             for (int i = 0; i < C; i++) dst[c * C + i] = pr[i];
                         }
                     };
-                    tc::static_for<0, NCH>(chunk);
-                    tr.commit();
+                    tc::static_for<0, NCH / NPASS>(chunk);
+                    if constexpr (NPASS == 2) {
+                        // every consumer warp has read the first half of the priors: one thread issues the second layer-3 pass
+                        // into the same columns (h2 is still in the slot's A columns), then all wait for it
+                        asm volatile("tcgen05.fence::before_thread_sync;");
+                        asm volatile("bar.sync 3, %0;" ::"n"(32 * tc::kConsWarps));
+                        if (warp == kConsFirst && tc::elect_one()) {
+                            asm volatile("tcgen05.fence::after_thread_sync;");
+                            issue_layer3_merged(ts, 1);
+                            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                                smem_addr(&d2_full[slot])));
+                        }
+                        __syncwarp();
+                        tc::mbar_wait<MVN_CONS_PARK>(smem_addr(&d2_full[slot]), (NPASS * use + 1) & 1, timeout_flag);
+                        asm volatile("tcgen05.fence::after_thread_sync;");
+                        tc::static_for<NCH / NPASS, NCH>(chunk);
+                    }
+                    if (active) tr.commit();
                     if constexpr (MLSE) surv.put(t0 + tt, sv, t0 + tt == p.n_stages - 1);
                     TC_TRACE(13, warp == kConsFirst && lane == 0);
                 }
                 __syncwarp();
-                if constexpr (!MLSE) emit(t0, bits);
+                if constexpr (!MLSE) {
+                    if (active) emit(t0, bits);
+                }
             }
             if constexpr (MLSE) {
                 __syncwarp();
@@ -615,7 +660,7 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
                 __syncwarp();
             }
             if (p.target) {
-                const bool counted = b < p.B && !(p.pilot_period > 0 && b % p.pilot_period == 0);
+                const bool counted = active && b < p.B && !(p.pilot_period > 0 && b % p.pilot_period == 0);
                 if (counted) {
                     acc.bit_errs += frame_bit_errs;
                     acc.frame_errs += frame_bit_errs ? 1u : 0u;
@@ -633,9 +678,9 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
 
 template <int L>
 constexpr size_t tc_smem_bytes() {   // + the consumers' survivor masks in MLSE mode (launch_tc)
-    return size_t(tc::kBBytes) + tc::b2_bytes(1 << L) +
-           (size_t(tc::kProdWarps + tc::kConsWarps) * kTileFloats + 4 * (tc::kK / 2)) * sizeof(float) +
-           (L > 5 ? SmemTrellis<L>::bytes(32 * tc::kConsWarps) : 0);
+    constexpr int kQ = (L == 8) ? 2 : 4;   // active lane quadrants (see the kernel)
+    return size_t(tc::kBBytes) + tc::b2_bytes(1 << L) + (size_t(4 * kQ) * kTileFloats + 4 * (tc::kK / 2)) * sizeof(float) +
+           (L > 5 ? SmemTrellis<L>::bytes(32 * kQ) : 0);
 }
 
 }  // namespace mvn

@@ -46,10 +46,10 @@ def main():
         print(f'L={L} NT={nt}: loop {len(loop)} instrs, FFMA2 {c["FFMA2"]}, LDCU {c["LDCU"]}, LDC {c["LDC"]}, '
               f'MOV {c["MOV"] + c["IMAD"]} -> {"ok" if good else "FALLBACK TO LDC"}')
         ok &= good
-    # tcgen05 kernel (default for L <= 6): tensor-core and TMEM instructions present, MMAs issued back to back
+    # tcgen05 kernel (default for every L): tensor-core and TMEM instructions present, MMAs issued back to back
     # (elect.sync form: no per-MMA ELECT / R2UR / BRA.U.ANY serialisation loop)
-    for L in range(1, 7):
-        body = next((f for f in funcs if f.startswith(f'_ZN3mvn21vnet_decode_tc_kernelILi{L}E')), None)
+    for L in range(1, 9):
+        body = next((f for f in funcs if f.startswith(f'_ZN3mvn21vnet_decode_tc_kernelILi{L}ELb0E')), None)
         if body is None:
             print(f'tcgen05 L={L}: kernel not found')
             ok = False
