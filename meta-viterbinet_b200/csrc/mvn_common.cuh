@@ -243,17 +243,25 @@ struct SmemTrellis {
         return bit;
     }
     __device__ __forceinline__ uint32_t step_chunk_rt(int c, const float (&cost)[C]) {
+        // all loads of the chunk first, then the arithmetic, then the stores: the compiler must assume that a store to the
+        // next-metrics buffer aliases the following loads of the current one, so an interleaved loop serialises on the
+        // shared-memory latency of every pair (measured: ~400 cycles per 16-state chunk)
+        float old_[C];
+#pragma unroll
+        for (int i = 0; i < C; i++) old_[i] = at(cur, (c * C + i) % H);
         uint32_t surv = 0;
+        float v[C / 2];
 #pragma unroll
         for (int i = 0; i < C / 2; i++) {
-            const float a = at(cur, (c * C + 2 * i) % H) + cost[2 * i];
-            const float b = at(cur, (c * C + 2 * i + 1) % H) + cost[2 * i + 1];
-            const float v = fminf(a, b);
-            at(cur ^ 1, c * (C / 2) + i) = v;
-            if (i & 1) no = fminf(no, v);   // new state c*(C/2)+i: C/2 is even for every trellis kept in shared memory
-            else ne = fminf(ne, v);
+            const float a = old_[2 * i] + cost[2 * i];
+            const float b = old_[2 * i + 1] + cost[2 * i + 1];
+            v[i] = fminf(a, b);
+            if (i & 1) no = fminf(no, v[i]);   // new state c*(C/2)+i: C/2 is even for every trellis kept in shared memory
+            else ne = fminf(ne, v[i]);
             surv |= uint32_t(b < a) << i;
         }
+#pragma unroll
+        for (int i = 0; i < C / 2; i++) at(cur ^ 1, c * (C / 2) + i) = v[i];
         return surv;
     }
     __device__ __forceinline__ void commit() {
@@ -262,6 +270,68 @@ struct SmemTrellis {
         ne = no = 3.0e38f;
     }
     __device__ __forceinline__ float metric(int h) const { return at(cur, h); }
+};
+
+// Same trellis with the column count known at compile time and two base pointers swapped at commit: every access of a
+// fully unrolled stage is one LDS / STS with an immediate offset (the generic form above pays an address computation per
+// access).  Used by the consumer warps of the tensor-core kernel.
+template <int L, int NCOLS>
+struct SmemTrellisFixed {
+    static constexpr int S = TrellisDims<L>::S, H = TrellisDims<L>::H, C = TrellisDims<L>::C;
+    float *cur_p, *nxt_p;   // &array[buf][0][col]
+    float e, o, ne, no;
+    __device__ __forceinline__ void init(float *array, int /*ncols*/, int col) {
+        cur_p = array + col;
+        nxt_p = array + size_t(H) * NCOLS + col;
+    }
+    static __host__ __device__ constexpr size_t bytes(int) { return size_t(2) * H * NCOLS * sizeof(float); }
+    __device__ __forceinline__ void reset() {
+#pragma unroll 8
+        for (int h = 0; h < H; h++) cur_p[h * NCOLS] = 0.f;
+        e = o = 0.f;
+        ne = no = 3.0e38f;
+    }
+    __device__ __forceinline__ uint32_t decide() const {
+        if (o != e) return o < e ? 1u : 0u;
+        float best = cur_p[0];
+        uint32_t bit = 0;
+#pragma unroll 8
+        for (int h = 1; h < H; h++) {
+            const float v = cur_p[h * NCOLS];
+            const bool lt = v < best;
+            best = fminf(best, v);
+            bit = lt ? uint32_t(h & 1) : bit;
+        }
+        return bit;
+    }
+    template <int c>
+    __device__ __forceinline__ uint32_t step_chunk(const float (&cost)[C]) {
+        float old_[C];   // loads, then arithmetic, then stores (see SmemTrellis::step_chunk_rt)
+#pragma unroll
+        for (int i = 0; i < C; i++) old_[i] = cur_p[((c * C + i) % H) * NCOLS];
+        uint32_t surv = 0;
+        float v[C / 2];
+#pragma unroll
+        for (int i = 0; i < C / 2; i++) {
+            const float a = old_[2 * i] + cost[2 * i];
+            const float b = old_[2 * i + 1] + cost[2 * i + 1];
+            v[i] = fminf(a, b);
+            if (i & 1) no = fminf(no, v[i]);
+            else ne = fminf(ne, v[i]);
+            surv |= uint32_t(b < a) << i;
+        }
+#pragma unroll
+        for (int i = 0; i < C / 2; i++) nxt_p[(c * (C / 2) + i) * NCOLS] = v[i];
+        return surv;
+    }
+    __device__ __forceinline__ void commit() {
+        float *t = cur_p;
+        cur_p = nxt_p;
+        nxt_p = t;
+        e = ne, o = no;
+        ne = no = 3.0e38f;
+    }
+    __device__ __forceinline__ float metric(int h) const { return cur_p[h * NCOLS]; }
 };
 
 // ---------------------------------------------------------------- packed fp32x2 helpers (sm_100)

@@ -452,7 +452,9 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
                     for (int i = 0; i < 2; i++) tc::compute_chunk<false>(sP_addr, c_base + i, yy, vh[i], vl[i]);
                     if (last_step) tc::compute_chunk<true>(sP_addr, 6, yy, vh[2], vl[2]);
                     TC_TRACE(1, tid == 0);
-                    tc::mbar_wait<MVN_PROD_PARK>(smem_addr(&slot_free[slot]), (use & 1) ^ 1, timeout_flag);
+                    // (128 / 256 states are bound by the consumers: there the producers park instead of polling, which
+                    //  would take issue slots from the consumer warp on their scheduler)
+                    tc::mbar_wait<(MVN_PROD_PARK || L >= 7)>(smem_addr(&slot_free[slot]), (use & 1) ^ 1, timeout_flag);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     TC_TRACE(2, tid == 0);
 #pragma unroll
