@@ -552,7 +552,7 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
         // MLSE: no running decision; the S/2 survivor bits of every stage go to this warp's shared-memory masks and the
         // frame is traced back in the kernel once its last stage is through (the producers are already two stages into the
         // next tile by then, so the traceback overlaps their work).
-        typename std::conditional<(L <= 5), RegTrellis<L>, SmemTrellis<L>>::type tr;
+        typename std::conditional<(L <= 5), RegTrellis<L>, SmemTrellisFixed<L, 32 * kQ>>::type tr;
         float *after_w3 = reinterpret_cast<float *>(sB2 + kB2Bytes);
         if constexpr (L > 5) {  // path metrics of the frames of the tile: [2][H][32 kQ] floats behind the W3 pieces
             tr.init(after_w3, 32 * kQ, (active ? quad : 0) * 32 + lane);
@@ -620,8 +620,7 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
                             cost[i] = -pr[i];
                         }
                         uint32_t s8;
-                        if constexpr (L <= 5) s8 = tr.template step_chunk<c>(cost);
-                        else s8 = tr.step_chunk_rt(c, cost);
+                        s8 = tr.template step_chunk<c>(cost);
                         if constexpr (MLSE) sv |= s8 << ((c * (C / 2)) & 31);
                         if (dst) {
 #pragma unroll
