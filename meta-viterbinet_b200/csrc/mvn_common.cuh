@@ -538,4 +538,14 @@ __device__ __forceinline__ unsigned tile_bit_errors(const float *tile_row, uint3
     return e;
 }
 
+// same straight from global memory (kernels that stage no target tile): loads beyond the row are not issued
+__device__ __forceinline__ unsigned row_bit_errors_global(const float *__restrict__ row, uint32_t bits, int valid_cols) {
+    unsigned e = 0;
+#pragma unroll 8
+    for (int c = 0; c < 32; c++) {
+        if (c < valid_cols) e += (int(__ldg(row + c)) != int((bits >> c) & 1u)) ? 1u : 0u;
+    }
+    return e;
+}
+
 }  // namespace mvn

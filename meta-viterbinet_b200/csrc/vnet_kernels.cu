@@ -343,7 +343,7 @@ static int launch_tc_mode(VnetParams p, cudaStream_t st) {
     auto kern = vnet_decode_tc_kernel<L, MLSE>;
     MVN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     p.n_warp_tiles = (p.B + 31) / 32;
-    constexpr int kQ = (L == 8) ? 2 : 4;   // 32-frame warp tiles per CTA tile
+    constexpr int kQ = 4;                  // 32-frame warp tiles per CTA tile
     const int64_t need = (p.n_warp_tiles + kQ - 1) / kQ;
     const int grid = int(std::min<int64_t>(need, sm_count()));
     int dev = 0;
@@ -412,7 +412,7 @@ static int launch_fused(const VnetParams &p, cudaStream_t st) {
 
 // frames decoded by one full wave of CTAs (host pipeline chunk sizing)
 int vnet_frames_per_wave(int L, int variant) {
-    const int per_cta = !(variant == 1 || variant == 2 || variant == 4) ? (L == 8 ? 64 : 128)
+    const int per_cta = !(variant == 1 || variant == 2 || variant == 4) ? 128
                         : L <= 3 ? 448 * 2 : L <= 5 ? 384 * 2 : L <= 7 ? 128 * 2 : 128;
     return per_cta * sm_count();
 }

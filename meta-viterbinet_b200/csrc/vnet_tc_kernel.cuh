@@ -305,12 +305,14 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
     //         the tensor core itself (scale-input-d: D = A B + D 2^-11): ONE 128-column accumulator.
     // L == 8: 256 priors go through the same 128 columns in TWO layer-3 passes per stage (states 0..127, then 128..255:
     //         the stage loop consumes the source states in that order anyway); the second pass is issued by a consumer
-    //         thread once all consumer warps have read the first half.  The 256-state path metrics of 128 frames (131 KB)
-    //         do not fit shared memory next to W3's fp16 pieces (64 KB), so a CTA tile is 64 frames: TMEM lane quadrants
-    //         0 and 1 work, the warps of quadrants 2 and 3 only keep the barrier protocol in step.
+    //         thread once all consumer warps have read the first half.  W3's fp16 pieces (64 KB) and the 256-state path
+    //         metrics of the 128 frames (128 KB) fill the shared memory, so this instance stages no tiles at all: the
+    //         producers read their sample straight from global memory (one L1-resident line per frame and 32 stages),
+    //         the consumers their targets.
     constexpr bool MERGED = (L >= 7);
     constexpr int NPASS = (L == 8) ? 2 : 1;      // layer-3 passes per stage
-    constexpr int kQ = (L == 8) ? 2 : 4;         // active TMEM lane quadrants = 32-frame warp tiles per CTA tile
+    constexpr int kQ = 4;                        // active TMEM lane quadrants = 32-frame warp tiles per CTA tile
+    constexpr bool DIRECT = (L == 8);            // no staged tiles (see above)
     using D = TrellisDims<L>;
     constexpr int S = D::S, C = D::C, NCH = D::NCH, NW = tc::kProdWarps + tc::kConvWarps + tc::kConsWarps;
     constexpr int N2 = tc::n2_of(S), kB2Bytes = tc::b2_bytes(S);
@@ -319,7 +321,7 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(8) uint64_t d_full[2], slot_free[2], a_full[2], d2_full[2];
-    constexpr int NT_TILES = 4 * kQ;                                             // active producers (3 per quadrant) and consumers stage tiles
+    constexpr int NT_TILES = DIRECT ? 0 : 4 * kQ;                                // producers (3 per quadrant) and consumers stage tiles
     uint8_t *sB = smem_raw;                                                      // W2 pieces, hi rows | lo rows
     float *tiles = reinterpret_cast<float *>(smem_raw + tc::kBBytes);            // one 32x32 tile per such warp
     float *sP = tiles + NT_TILES * kTileFloats;                                  // [56][4] pair table for the packed sigmoid
@@ -330,7 +332,7 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
     const bool mma_warp = warp == NW;
     // tiles: one per producer warp (y) and one per consumer warp (targets); converters and the MMA warp use none
     const bool active = quad < kQ;
-    float *tile = tiles + (producer ? (warp >> 2) * kQ + (active ? quad : 0) : 3 * kQ + (active ? quad : 0)) * kTileFloats;
+    float *tile = tiles + (DIRECT ? 0 : (producer ? (warp >> 2) * kQ + (active ? quad : 0) : 3 * kQ + (active ? quad : 0)) * kTileFloats);
 
     // ---- W2 (and b2 as column k=100) -> fp16 hi / scaled-lo pieces in the canonical K-major layout
     for (int idx = tid; idx < tc::kN * tc::kK; idx += tc::kThreadsTc) {
@@ -429,12 +431,13 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
                     }
                     continue;
                 }
-                warp_load_tile(p.y, p.B, p.T, p.T, row0, t0, tile, lane, vec_in);
+                if constexpr (!DIRECT) warp_load_tile(p.y, p.B, p.T, p.T, row0, t0, tile, lane, vec_in);
+                const float *yrow = p.y + (row0 + lane < p.B ? row0 + lane : 0) * int64_t(p.T) + t0;
 #pragma unroll 1
                 for (int tt = 0; tt < t_end; tt++, n++) {
                     const uint32_t slot = n & 1, use = n >> 1;
                     const uint32_t slot_lane = tmem + slot * tc::kSlotCols + lane_base;
-                    const float yv = tile[lane * kTileLd + tt];
+                    const float yv = DIRECT ? __ldg(yrow + tt) : tile[lane * kTileLd + tt];
                     const u64 yy = pack2(yv, yv);
                     // Compute this stage's pieces into registers BEFORE waiting for the slot: the sigmoid/split work
                     // then overlaps the MMAs and the consumer of the stage that still owns the slot.
@@ -575,9 +578,13 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
                         static_cast<uint32_t *>(p.decoded)[b * n_words + t0 / 32] = bits;
                 }
                 if (p.target && t0 < p.target_T) {
-                    warp_load_tile(p.target, p.B, p.target_T, p.target_T, row0, t0, tile, lane, vec_tgt);
-                    frame_bit_errs += tile_bit_errors(tile + lane * kTileLd, bits, p.target_T - t0);
-                    __syncwarp();
+                    if constexpr (DIRECT) {
+                        if (b < p.B) frame_bit_errs += row_bit_errors_global(p.target + b * p.target_T + t0, bits, p.target_T - t0);
+                    } else {
+                        warp_load_tile(p.target, p.B, p.target_T, p.target_T, row0, t0, tile, lane, vec_tgt);
+                        frame_bit_errs += tile_bit_errors(tile + lane * kTileLd, bits, p.target_T - t0);
+                        __syncwarp();
+                    }
                 }
             };
             for (int t0 = 0; t0 < p.T; t0 += 32) {
@@ -679,8 +686,8 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
 
 template <int L>
 constexpr size_t tc_smem_bytes() {   // + the consumers' survivor masks in MLSE mode (launch_tc)
-    constexpr int kQ = (L == 8) ? 2 : 4;   // active lane quadrants (see the kernel)
-    return size_t(tc::kBBytes) + tc::b2_bytes(1 << L) + (size_t(4 * kQ) * kTileFloats + 4 * (tc::kK / 2)) * sizeof(float) +
+    constexpr int kQ = 4;
+    return size_t(tc::kBBytes) + tc::b2_bytes(1 << L) + (size_t(L == 8 ? 0 : 4 * kQ) * kTileFloats + 4 * (tc::kK / 2)) * sizeof(float) +
            (L > 5 ? SmemTrellis<L>::bytes(32 * kQ) : 0);
 }
 

@@ -348,7 +348,7 @@ def test_error_rates_golden(mvn, k):
     assert np.array_equal(idx.cpu().numpy(), g[f'idx_{k}'])
 
 
-@pytest.mark.parametrize('L', [1, 4, 5, 6])
+@pytest.mark.parametrize('L', [1, 4, 5, 6, 7, 8])
 def test_vnet_fused_edge_shapes_with_counters(mvn, fused_impl, L):
     """no stage at all, one symbol, exact tile multiples, tile + 1, stages ending mid-tile; fused counters exact;
     the tensor-core kernel's pipeline-timeout flag stays clear"""
