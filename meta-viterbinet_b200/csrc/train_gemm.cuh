@@ -188,6 +188,21 @@ __host__ __device__ constexpr size_t act_floats(int ldn, bool tangent) {
     return size_t(kH1 + 2 * kH2P + Lay<S>::SP) * ldn * (tangent ? 2 : 1) + ldn;
 }
 
+// G[base + r[i] * ld + c[j]] += scale * v[i][j] for the valid rows / columns of a tile: all 16 loads, then the 16 stores
+// (a read-modify-write per element in one loop serialises: each store may alias the next load)
+__device__ __forceinline__ void accumulate_tile(float *__restrict__ Gbase, int ld, const Tile &t, const float (&v)[4][4], float scale) {
+    float g[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) g[i][j] = (t.r[i] >= 0 && t.c[j] >= 0) ? Gbase[t.r[i] * ld + t.c[j]] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (t.r[i] >= 0 && t.c[j] >= 0) Gbase[t.r[i] * ld + t.c[j]] = fmaf(scale, v[i][j], g[i][j]);
+}
+
 // sum of v over the 8 lanes that share lm (the lanes of one tile row), result in every lane
 __device__ __forceinline__ float sum_ln(float v) {
     v += __shfl_xor_sync(kFull, v, 1);
@@ -348,12 +363,7 @@ __device__ __forceinline__ float pass(const Smem<S> &sm, const float *__restrict
             if (!MERGE) {
                 for (int blk = warp; blk < nb3; blk += kWarps)
                     gemm_block<AK, BK, WM, true>(g3, blk, [&](const Tile &t, float (&acc)[4][4], float (&racc)[4][4]) {
-#pragma unroll
-                        for (int i = 0; i < 4; i++)
-#pragma unroll
-                            for (int j = 0; j < 4; j++)
-                                if (t.r[i] >= 0 && t.c[j] >= 0)
-                                    G[LY::w3 + t.r[i] * kH2P + t.c[j]] += scale * (TAN ? racc[i][j] : acc[i][j]);
+                        accumulate_tile(G + LY::w3, kH2P, t, TAN ? racc : acc, scale);
                     });
                 __syncthreads();
             }
@@ -382,12 +392,7 @@ __device__ __forceinline__ float pass(const Smem<S> &sm, const float *__restrict
                     });
                 } else {
                     gemm_block<AK, BK, WM, true>(g3, blk - nb4, [&](const Tile &t, float (&acc)[4][4], float (&racc)[4][4]) {
-#pragma unroll
-                        for (int i = 0; i < 4; i++)
-#pragma unroll
-                            for (int j = 0; j < 4; j++)
-                                if (t.r[i] >= 0 && t.c[j] >= 0)
-                                    G[LY::w3 + t.r[i] * kH2P + t.c[j]] += scale * (TAN ? racc[i][j] : acc[i][j]);
+                        accumulate_tile(G + LY::w3, kH2P, t, TAN ? racc : acc, scale);
                     });
                 }
             }
@@ -434,12 +439,7 @@ __device__ __forceinline__ float pass(const Smem<S> &sm, const float *__restrict
                     });
                 } else {
                     gemm_block<AK, BK, WM, true>(g5, blk - nb6, [&](const Tile &t, float (&acc)[4][4], float (&racc)[4][4]) {
-#pragma unroll
-                        for (int i = 0; i < 4; i++)
-#pragma unroll
-                            for (int j = 0; j < 4; j++)
-                                if (t.r[i] >= 0 && t.c[j] >= 0)
-                                    G[LY::w2 + t.r[i] * kH1 + t.c[j]] += scale * (TAN ? racc[i][j] : acc[i][j]);
+                        accumulate_tile(G + LY::w2, kH1, t, TAN ? racc : acc, scale);
                     });
                 }
             }
