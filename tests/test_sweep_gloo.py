@@ -70,3 +70,16 @@ def test_partition_and_work_items():
         for w in (1, 2, 3, 4, 6, 8):
             items = sweep.work_items(points, w)
             assert len({len(sweep.partition(len(items), w, r)) for r in range(w)}) == 1, (points, w)
+
+
+def test_before_reduce_hook_runs_once_after_the_last_block():
+    """run_sweep(before_reduce=...) — where a caller that spreads its launches over several streams joins them"""
+    calls = []
+
+    def block(point, first, n, row):
+        calls.append(('block', point, first, n))
+        row += torch.tensor([0, 0, n * 10, n])
+
+    total = sweep.run_sweep([7, 8, 9], 100, block, rank=0, world_size=1, before_reduce=lambda: calls.append(('join',)))
+    assert calls[-1] == ('join',) and sum(1 for c in calls if c[0] == 'join') == 1 and len(calls) == 4
+    assert total[:, 3].tolist() == [100, 100, 100]
