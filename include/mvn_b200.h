@@ -155,6 +155,7 @@ typedef struct mvn_ctx mvn_ctx;
 /* chunk_frames <= 0 selects two full waves of the fused kernel per chunk. */
 int mvn_ctx_create(mvn_ctx **ctx, int device, int64_t chunk_frames, int T_max, int L);
 void mvn_ctx_destroy(mvn_ctx *ctx);
+/* (pageable source arrays may be reused as soon as the call returns; pinned ones after the next synchronising call) */
 int mvn_ctx_set_vnet_weights_host(mvn_ctx *ctx, const float *w1, const float *b1, const float *w2,
                                   const float *b2, const float *w3, const float *b3);
 int mvn_ctx_vnet_decode_host(mvn_ctx *ctx, const float *y_host, int64_t B, int T, int n_stages,
