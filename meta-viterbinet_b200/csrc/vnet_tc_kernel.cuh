@@ -48,7 +48,17 @@ constexpr int kM = 128, kN = 64, kK = 112;    // MMA tile: frames x padded outpu
 constexpr int kKSteps = kK / 16;              // UMMA_K = 16 for fp16
 constexpr int kACols = kK / 2;                // 32-bit TMEM columns per A piece (two fp16 per column)
 constexpr int kSlotCols = 256;                // slot stride; 240 used: D_main | D_corr | A_hi | A_lo
-constexpr int oDm = 0, oDc = kN, oAh = 2 * kN, oAl = 2 * kN + kACols;
+constexpr int oDm = 0, oDc = kN, oAh = 2 * kN, oAl = 2 * kN + kACols;   // round-1 layout (L >= 7): D_main | D_corr | A_hi | A_lo
+// Decoupled layout (L <= 6): ONE 64-column accumulator for layer 2 (its correction chain is folded in on the tensor core
+// with scale-input-d) leaves room for h2 columns of their own, so the producers' A columns are free again as soon as the
+// layer-2 MMAs have read them — the producers no longer wait for the consumers of the stage two back.
+//   D (64) | A_hi (56) | A_lo (56) | H2_hi (32) | H2_lo (32)   = 240 columns
+template <bool DEC>
+struct Lay {
+    static constexpr int D = 0;
+    static constexpr int Ah = DEC ? kN : 2 * kN, Al = Ah + kACols;
+    static constexpr int Hh = DEC ? Al + kACols : Ah, Hl = DEC ? Hh + 32 : Al;   // layer-3 A operand (round-1 layout: inside A)
+};
 constexpr float kScale = 2048.f, kInvScale = 1.f / 2048.f;
 // B operand of layer 2: the hi and lo pieces of W2 stacked along N (rows 0..63 hi, 64..127 lo), so ONE N=128 MMA per
 // k-step produces D_main | D_corr side by side; the A_lo x B_hi chain reads rows 0..63 of the same buffer (N=64).
@@ -252,12 +262,14 @@ __device__ __forceinline__ void compute_chunk(uint32_t sP_addr, int c0, u64 yy, 
 // converter warps: h2 = relu(D_main + D_corr / 2048) of this thread's frame, split into fp16 hi / scaled lo,
 // stored as the A operand of layer 3 (columns 0..31 of the slot's A_hi / A_lo regions, free after the MMAs of
 // layer 2); column k2 = 50 is the constant 1 that multiplies the b3 row of B2.
+template <bool DEC>
 __device__ __forceinline__ void h2_to_tmem(uint32_t slot_lane) {
+    using LY = Lay<DEC>;
 #pragma unroll
     for (int c0 = 0; c0 < kK2Steps; c0++) {   // 16 hidden units = 8 columns per step
         float m[16], c[16];
         tmem_ld16(slot_lane + oDm + 16 * c0, m);
-        tmem_ld16(slot_lane + oDc + 16 * c0, c);
+        if (!DEC) tmem_ld16(slot_lane + oDc + 16 * c0, c);   // (DEC: the accumulator already holds 2048 (W2 h1 + b2))
         asm volatile("tcgen05.wait::ld.sync.aligned;");
         uint32_t vh[8], vl[8];
 #pragma unroll
@@ -266,14 +278,16 @@ __device__ __forceinline__ void h2_to_tmem(uint32_t slot_lane) {
             if (k + 1 < kH2) {
                 // D_main + D_corr / 2048 = 2048 (W2 h1 + b2), both units of the pair in one packed FMA; ReLU and the
                 // hi / lo split in split2_relu
-                split2_relu(fma2(pack2(c[2 * q], c[2 * q + 1]), 0x3a0000003a000000ull, pack2(m[2 * q], m[2 * q + 1])), vh[q], vl[q]);
+                const u64 X = DEC ? pack2(m[2 * q], m[2 * q + 1])
+                                  : fma2(pack2(c[2 * q], c[2 * q + 1]), 0x3a0000003a000000ull, pack2(m[2 * q], m[2 * q + 1]));
+                split2_relu(X, vh[q], vl[q]);
             } else {  // k2 = 50: bias column (1.0 in the low half); beyond: zero padding
                 vh[q] = (k == kH2) ? 0x00003c00u : 0u;
                 vl[q] = 0u;
             }
         }
-        tmem_st8(slot_lane + oAh + c0 * 8, vh);
-        tmem_st8(slot_lane + oAl + c0 * 8, vl);
+        tmem_st8(slot_lane + LY::Hh + c0 * 8, vh);
+        tmem_st8(slot_lane + LY::Hl + c0 * 8, vl);
     }
     asm volatile("tcgen05.wait::st.sync.aligned;");
 }
@@ -309,7 +323,9 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
     //         metrics of the 128 frames (128 KB) fill the shared memory, so this instance stages no tiles at all: the
     //         producers read their sample straight from global memory (one L1-resident line per frame and 32 stages),
     //         the consumers their targets.
-    constexpr bool MERGED = (L >= 7);
+    constexpr bool DEC = (L <= 6);               // decoupled TMEM layout (tc::Lay): merged layer-2 accumulator, own h2 columns
+    using LY = tc::Lay<DEC>;
+    constexpr bool MERGED = (L >= 6);            // layer-3 correction chain folded into the main accumulator (64..128 columns)
     constexpr int NPASS = (L == 8) ? 2 : 1;      // layer-3 passes per stage
     constexpr int kQ = 4;                        // active TMEM lane quadrants = 32-frame warp tiles per CTA tile
     constexpr bool DIRECT = (L == 8);            // no staged tiles (see above)
@@ -403,16 +419,16 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
         const uint32_t rows = uint32_t(half) * (N3 / 8) * 128;
 #pragma unroll
         for (int j = 0; j < tc::kK2Steps; j++)   // corr = h2_hi W3_lo
-            tc::mma_f16_ts(ts + tc::oDm, ts + tc::oAh + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2 + kLoRows + rows, kLBO2),
+            tc::mma_f16_ts(ts + tc::oDm, ts + LY::Hh + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2 + kLoRows + rows, kLBO2),
                            idesc2, j > 0);
 #pragma unroll
         for (int j = 0; j < tc::kK2Steps; j++)   // corr += h2_lo W3_hi
-            tc::mma_f16_ts(ts + tc::oDm, ts + tc::oAl + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2 + rows, kLBO2), idesc2, 1);
+            tc::mma_f16_ts(ts + tc::oDm, ts + LY::Hl + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2 + rows, kLBO2), idesc2, 1);
         // priors = h2_hi W3_hi + corr / 2048: the first MMA of the main chain reads D scaled by 2^-11
-        tc::mma_f16_ts_scale11(ts + tc::oDm, ts + tc::oAh, tc::b_desc(sB2_addr + rows, kLBO2), idesc2);
+        tc::mma_f16_ts_scale11(ts + tc::oDm, ts + LY::Hh, tc::b_desc(sB2_addr + rows, kLBO2), idesc2);
 #pragma unroll
         for (int j = 1; j < tc::kK2Steps; j++)
-            tc::mma_f16_ts(ts + tc::oDm, ts + tc::oAh + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2 + rows, kLBO2), idesc2, 1);
+            tc::mma_f16_ts(ts + tc::oDm, ts + LY::Hh + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2 + rows, kLBO2), idesc2, 1);
     };
 
     if (producer) {
@@ -457,17 +473,19 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
                     TC_TRACE(1, tid == 0);
                     // (128 / 256 states are bound by the consumers: there the producers park instead of polling, which
                     //  would take issue slots from the consumer warp on their scheduler)
-                    tc::mbar_wait<(MVN_PROD_PARK || L >= 7)>(smem_addr(&slot_free[slot]), (use & 1) ^ 1, timeout_flag);
+                    // DEC: the A columns are free once the layer-2 MMAs of the slot's previous use have read them (d_full);
+                    // round-1 layout: once the consumers have released the slot (h2 lives in the A columns)
+                    tc::mbar_wait<(MVN_PROD_PARK || L >= 7)>(smem_addr(DEC ? &d_full[slot] : &slot_free[slot]), (use & 1) ^ 1, timeout_flag);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     TC_TRACE(2, tid == 0);
 #pragma unroll
                     for (int i = 0; i < 2; i++) {
-                        tc::tmem_st8(slot_lane + tc::oAh + (c_base + i) * 8, vh[i]);
-                        tc::tmem_st8(slot_lane + tc::oAl + (c_base + i) * 8, vl[i]);
+                        tc::tmem_st8(slot_lane + LY::Ah + (c_base + i) * 8, vh[i]);
+                        tc::tmem_st8(slot_lane + LY::Al + (c_base + i) * 8, vl[i]);
                     }
                     if (last_step) {
-                        tc::tmem_st8(slot_lane + tc::oAh + 6 * 8, vh[2]);
-                        tc::tmem_st8(slot_lane + tc::oAl + 6 * 8, vl[2]);
+                        tc::tmem_st8(slot_lane + LY::Ah + 6 * 8, vh[2]);
+                        tc::tmem_st8(slot_lane + LY::Al + 6 * 8, vl[2]);
                     }
                     rot = rot == 2 ? 0 : rot + 1;
                     asm volatile("tcgen05.wait::st.sync.aligned;");
@@ -492,15 +510,35 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
                     tc::mbar_wait(smem_addr(&a_full[slot]), use & 1, timeout_flag);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     TC_TRACE(4, lane == 0);
+                    if constexpr (DEC) {   // the accumulator columns also carry the priors of the slot's previous use: wait for its consumers
+                        tc::mbar_wait(smem_addr(&slot_free[slot]), (use & 1) ^ 1, timeout_flag);
+                        asm volatile("tcgen05.fence::after_thread_sync;");
+                    }
                     if (tc::elect_one()) {
                         const uint32_t ts = tmem + slot * tc::kSlotCols;
+                        if constexpr (!DEC) {
 #pragma unroll
-                        for (int j = 0; j < tc::kKSteps; j++)   // D_main | D_corr = A_hi [B_hi | B_lo]
-                            tc::mma_f16_ts(ts + tc::oDm, ts + tc::oAh + j * 8, tc::b_desc(sB_addr + uint32_t(2 * j) * tc::kLBO), idescw,
-                                           j > 0);
+                            for (int j = 0; j < tc::kKSteps; j++)   // D_main | D_corr = A_hi [B_hi | B_lo]
+                                tc::mma_f16_ts(ts + tc::oDm, ts + LY::Ah + j * 8, tc::b_desc(sB_addr + uint32_t(2 * j) * tc::kLBO), idescw,
+                                               j > 0);
 #pragma unroll
-                        for (int j = 0; j < tc::kKSteps; j++)   // D_main += A_lo B_hi (the remainder of the pre-scaled A is unscaled)
-                            tc::mma_f16_ts(ts + tc::oDm, ts + tc::oAl + j * 8, tc::b_desc(sB_addr + uint32_t(2 * j) * tc::kLBO), idesc, 1);
+                            for (int j = 0; j < tc::kKSteps; j++)   // D_main += A_lo B_hi (the remainder of the pre-scaled A is unscaled)
+                                tc::mma_f16_ts(ts + tc::oDm, ts + LY::Al + j * 8, tc::b_desc(sB_addr + uint32_t(2 * j) * tc::kLBO), idesc, 1);
+                        } else {
+                            constexpr uint32_t kLoRowsB = (tc::kN / 8) * 128;   // W2_lo rows inside a k-chunk of the stacked B
+#pragma unroll
+                            for (int j = 0; j < tc::kKSteps; j++)   // D = A_hi B_lo (the 2048-scaled correction)
+                                tc::mma_f16_ts(ts + tc::oDm, ts + LY::Ah + j * 8, tc::b_desc(sB_addr + uint32_t(2 * j) * tc::kLBO + kLoRowsB), idesc,
+                                               j > 0);
+                            // D = A_hi B_hi + D / 2048: scale-input-d on the first MMA of the main chain
+                            tc::mma_f16_ts_scale11(ts + tc::oDm, ts + LY::Ah, tc::b_desc(sB_addr), idesc);
+#pragma unroll
+                            for (int j = 1; j < tc::kKSteps; j++)
+                                tc::mma_f16_ts(ts + tc::oDm, ts + LY::Ah + j * 8, tc::b_desc(sB_addr + uint32_t(2 * j) * tc::kLBO), idesc, 1);
+#pragma unroll
+                            for (int j = 0; j < tc::kKSteps; j++)   // D += A_lo B_hi (the remainder of the pre-scaled A is unscaled)
+                                tc::mma_f16_ts(ts + tc::oDm, ts + LY::Al + j * 8, tc::b_desc(sB_addr + uint32_t(2 * j) * tc::kLBO), idesc, 1);
+                        }
                         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                             smem_addr(&d_full[slot])));
                     }
@@ -523,7 +561,7 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
                     tc::mbar_wait<MVN_CONS_PARK>(smem_addr(&d_full[slot]), use & 1, timeout_flag);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     TC_TRACE(7, warp == tc::kProdWarps && lane == 0);
-                    if (active) tc::h2_to_tmem(slot_lane);
+                    if (active) tc::h2_to_tmem<DEC>(slot_lane);
                     asm volatile("tcgen05.fence::before_thread_sync;");
                     TC_TRACE(8, warp == tc::kProdWarps && lane == 0);
                     asm volatile("bar.sync 2, %0;" ::"n"(32 * tc::kConvWarps));
@@ -533,11 +571,11 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
                         if constexpr (!MERGED) {   // 4 + 4 MMAs
 #pragma unroll
                             for (int j = 0; j < tc::kK2Steps; j++)   // priors_main | priors_corr = h2_hi [W3_hi | W3_lo]
-                                tc::mma_f16_ts(ts + tc::oDm, ts + tc::oAh + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2, kLBO2),
+                                tc::mma_f16_ts(ts + tc::oDm, ts + LY::Hh + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2, kLBO2),
                                                idesc2w, j > 0);
 #pragma unroll
                             for (int j = 0; j < tc::kK2Steps; j++)   // priors_corr += h2_lo W3_hi
-                                tc::mma_f16_ts(ts + tc::oDm + N2, ts + tc::oAl + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2, kLBO2),
+                                tc::mma_f16_ts(ts + tc::oDm + N2, ts + LY::Hl + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2, kLBO2),
                                                idesc2, 1);
                         } else {                   // 4 + 4 + 4 MMAs of N = 128 into one accumulator (pass 0: states 0..127)
                             issue_layer3_merged(ts, 0);
