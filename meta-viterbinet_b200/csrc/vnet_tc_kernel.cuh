@@ -1,35 +1,36 @@
-// tcgen05 variant of the fused ViterbiNet kernel (memory_length <= 6): layers 2 and 3 of the priors MLP
+// tcgen05 variant of the fused ViterbiNet kernel (memory_length 1..8, the default): layers 2 and 3 of the priors MLP
 // ([symbols,100] x [100,50] and [symbols,50] x [50,S], 99 % of the flops) run on the 5th-generation tensor cores;
 // the sigmoid, the ReLU / operand splits, the ACS recursion and the decision stay on the CUDA cores of the same CTA.
 //
 // fp32 parity on fp16 tensor cores.  Each operand is split into two fp16 pieces with a scaled remainder,
 //     x = hi + lo / 2048,   hi = fp16(x),   lo = fp16((x - hi) * 2048)      (x - hi is exact in fp32),
-// and   h1 . w = hi_h hi_w + (hi_h lo_w + lo_h hi_w) / 2048 + O(2^-22 |h1||w|)   is accumulated in fp32 by
-// two accumulators in TMEM: D_main (one chain of kind::f16 MMAs) and D_corr (two chains); fp16 products are
-// exact in fp32 and the 2^11 scaling keeps the remainders normal.  On the reference's fixtures the priors are
-// 2.4e-7 of the row maximum away from fp64 — closer than a plain fp32 dot product (4.4e-7), see DESIGN.md §5.1.
+// and   h1 . w = hi_h hi_w + (hi_h lo_w + lo_h hi_w) / 2048 + O(2^-22 |h1||w|)   is accumulated in fp32 in TMEM;
+// fp16 products are exact in fp32 and the 2^11 scaling keeps the remainders normal.  The correction chains either get
+// an accumulator of their own (D_corr, combined with D_main by the reader) or run first and are folded into the main
+// chain by the tensor core (scale-input-d: D = A B + D 2^-11).  On the reference's fixtures the priors are 2.4e-7 of the
+// row maximum away from fp64 — closer than a plain fp32 dot product (4.4e-7), see DESIGN.md §5.1.
 // (A first version used an exact three-way bf16 split with six chains: same accuracy, twice the tensor work.)
-// The bias b2 rides along as column k=100 of B against a constant column of A.
+// The biases ride along as a column of B against a constant column of A.
 // Layer 2 takes its A operand PRE-SCALED: the producers compute g = 2048 h1 directly (see denom2), so the remainder
-// g - fp16(g) is a normal fp16 number without a scaling multiply and goes to D_main; D_main + D_corr / 2048 is then
-// 2048 (W2 h1 + b2), which is what the ReLU / split of layer 3 wants as input.
+// g - fp16(g) is a normal fp16 number without a scaling multiply; the layer-2 result is then 2048 (W2 h1 + b2), which
+// is what the ReLU / split of layer 3 wants as input.
 //
 // Warp-specialised pipeline over a two-slot TMEM ring; one frame = one TMEM lane, 128 frames per CTA tile:
 //  12 producer warps : y -> 100 sigmoids -> fp16 hi/lo split -> tcgen05.st  A_hi, A_lo [128 x 112] (2 x 56 columns)
-//                      (three warps per TMEM lane quadrant serve the same 32 frames and split the hidden units)
-//   1 MMA warp       : per stage 7 + 7 tcgen05.mma.kind::f16 (M=128, K=16; N=128 for A_hi x [W2_hi | W2_lo], N=64 for
-//                      A_lo x W2_hi), A from TMEM, B from shared memory in the canonical K-major no-swizzle layout;
-//                      tcgen05.commit -> d_full[slot]
-//   4 converter warps: tcgen05.ld D_main/D_corr -> combine -> ReLU -> the same hi/lo split -> tcgen05.st as the A
-//                      operand of LAYER 3, which also runs on the tensor core (4 + 4 MMAs, W3 pieces and b3 in
-//                      shared memory, issued by one converter thread)
-//   4 consumer warps : tcgen05.ld of the 16 priors -> ACS on the frame's 8 private path metrics, decision bit,
-//                      outputs, BER.  Converters and consumers pipeline across the two slots: stage n+1 is converted
-//                      while layer 3 of stage n runs and its ACS is done.  No weight traffic on the LSU.
+//                      (three warps per TMEM lane quadrant serve the same 32 frames and split the hidden units; the
+//                       bias / padding columns are written once per launch)
+//   1 MMA warp       : the layer-2 tcgen05.mma.kind::f16 of a stage (M=128, K=16, N=64: A_hi x W2_lo, A_hi x W2_hi with
+//                      scale-input-d, A_lo x W2_hi = 21 MMAs; L >= 7: 7 of N=128 + 7 of N=64 into D_main | D_corr),
+//                      A from TMEM, B from shared memory in the canonical K-major no-swizzle layout; tcgen05.commit -> d_full
+//   4 converter warps: tcgen05.ld of the layer-2 result -> ReLU -> the same hi/lo split -> tcgen05.st as the A operand
+//                      of LAYER 3, which also runs on the tensor core (8-12 MMAs, W3 pieces and b3 in shared memory,
+//                      issued by one converter thread; 256 states: two passes)
+//   4 consumer warps : tcgen05.ld of the priors -> ACS on the frame's private path metrics, decision bit (or survivor
+//                      masks + in-kernel traceback), outputs, BER.  Converters and consumers pipeline across the two
+//                      slots: stage n+1 is converted while layer 3 of stage n runs and its ACS is done.
 // The sigmoid/split/MMA work of later stages does not depend on the ACS result of earlier ones (only the
 // decision chain is sequential), which is what lets producers and the tensor core run ahead.
-// TMEM: 2 x (64 + 64 + 56 + 56) columns of the 512-column allocation, one CTA per SM; layer 3 reuses the slot's
-// A columns for h2 and its D columns for the priors once layer 2's results have been read.
+// TMEM: 2 x 240 columns of the 512-column allocation, one CTA per SM; the slot layouts are described at tc::Lay.
 #pragma once
 #include <cuda_fp16.h>
 
@@ -40,6 +41,9 @@ namespace mvn {
 #ifndef MVN_PROD_PARK
 #define MVN_PROD_PARK false   // producers reach this wait with their stage computed: polling wakes them ~200 cycles sooner (+1 %)
 #endif
+#ifndef MVN_TC_MIXED_FMA
+#define MVN_TC_MIXED_FMA 0   // FHFMA (fma.f32.f16) in the hi/lo splits: one instruction less per pair, but measured 3 % SLOWER (L=4 17.1 -> 16.5 G sym/s)
+#endif
 #ifndef MVN_CONS_PARK
 #define MVN_CONS_PARK true
 #endif
@@ -49,15 +53,25 @@ constexpr int kKSteps = kK / 16;              // UMMA_K = 16 for fp16
 constexpr int kACols = kK / 2;                // 32-bit TMEM columns per A piece (two fp16 per column)
 constexpr int kSlotCols = 256;                // slot stride; 240 used: D_main | D_corr | A_hi | A_lo
 constexpr int oDm = 0, oDc = kN, oAh = 2 * kN, oAl = 2 * kN + kACols;   // round-1 layout (L >= 7): D_main | D_corr | A_hi | A_lo
-// Decoupled layout (L <= 6): ONE 64-column accumulator for layer 2 (its correction chain is folded in on the tensor core
-// with scale-input-d) leaves room for h2 columns of their own, so the producers' A columns are free again as soon as the
-// layer-2 MMAs have read them — the producers no longer wait for the consumers of the stage two back.
-//   D (64) | A_hi (56) | A_lo (56) | H2_hi (32) | H2_lo (32)   = 240 columns
-template <bool DEC>
+// TMEM layouts of one slot (240 of its 256 columns):
+//   mode 0 (L >= 7)      D_main (64) | D_corr (64) | A_hi (56) | A_lo (56); h2 reuses the first 32 columns of A_hi / A_lo,
+//                        so the producers may refill A only after the consumers have released the slot
+//   mode 1 ("merged")    D (64) | A_hi (56) | A_lo (56) | H2_hi (32) | H2_lo (32): ONE layer-2 accumulator (the correction
+//                        chain is folded in on the tensor core with scale-input-d, 21 MMAs of N = 64)
+//   mode 2 ("in place")  D_main | D_corr | A_hi | A_lo as mode 0 (7 MMAs of N = 128 + 7 of N = 64), but the converter writes
+//                        the h2 pieces of k-step j over the 16 D_corr columns it has just read (hi: 8 columns, lo: 8)
+// In modes 1 and 2 the A columns are free again as soon as the layer-2 MMAs have read them: the producers wait for d_full
+// of the slot's previous use, not for its consumers.
+#ifndef MVN_TC_LAYOUT
+#define MVN_TC_LAYOUT 1
+#endif
+template <int MODE>
 struct Lay {
     static constexpr int D = 0;
-    static constexpr int Ah = DEC ? kN : 2 * kN, Al = Ah + kACols;
-    static constexpr int Hh = DEC ? Al + kACols : Ah, Hl = DEC ? Hh + 32 : Al;   // layer-3 A operand (round-1 layout: inside A)
+    static constexpr int Ah = MODE == 1 ? kN : 2 * kN, Al = Ah + kACols;
+    // layer-3 A operand: TMEM column of the hi / lo piece of k-step j (16 hidden units = 8 columns)
+    __host__ __device__ static constexpr int hh(int j) { return MODE == 0 ? Ah + 8 * j : MODE == 1 ? Al + kACols + 8 * j : kN + 16 * j; }
+    __host__ __device__ static constexpr int hl(int j) { return MODE == 0 ? Al + 8 * j : MODE == 1 ? Al + kACols + 32 + 8 * j : kN + 16 * j + 8; }
 };
 constexpr float kScale = 2048.f, kInvScale = 1.f / 2048.f;
 // B operand of layer 2: the hi and lo pieces of W2 stacked along N (rows 0..63 hi, 64..127 lo), so ONE N=128 MMA per
@@ -67,8 +81,21 @@ constexpr float kScale = 2048.f, kInvScale = 1.f / 2048.f;
 constexpr uint32_t kLBO = (2 * kN / 8) * 128; // bytes between consecutive 16-byte K chunks (k-chunk stride)
 constexpr uint32_t kSBO = 128;                // bytes between 8-row groups along N
 constexpr int kBBytes = (kK / 8) * (2 * kN / 8) * 128;
-constexpr int kProdWarps = 12, kConvWarps = 4, kConsWarps = 4;   // producers | h2 converters | ACS consumers
-constexpr int kThreadsTc = 32 * (kProdWarps + kConvWarps + kConsWarps + 1);  // + one MMA-issue warp
+#ifndef MVN_TC_PROD_WARPS
+#define MVN_TC_PROD_WARPS 12   // 16 (four per quadrant, 72 registers) measured the same: the schedulers are issue-bound, not latency-bound
+#endif
+constexpr int kProdWarps = MVN_TC_PROD_WARPS, kConvWarps = 4, kConsWarps = 4;   // producers | h2 converters | ACS consumers
+constexpr int kProdParts = kProdWarps / 4;    // producer warps per TMEM lane quadrant (3 or 4)
+static_assert(kProdWarps == 12 || kProdWarps == 16, "24 double-pairs of hidden units split 8|8|8 or 6|6|6|6");
+// MMA-issue warps: stage n's layer-2 MMAs are issued by warp (n mod kMmaWarps) of them, its layer-3 MMAs by converter warp
+// ((n + 2) mod 4), so every scheduler (warp w runs on scheduler w mod 4, and serves TMEM lane quadrant w mod 4) carries
+// the same share of tcgen05.mma issue.  With ONE issue warp the pipeline trace showed the three producer warps on its
+// scheduler a full stage behind the other nine: a tcgen05.mma waiting for the tensor pipe holds up its scheduler.
+#ifndef MVN_TC_MMA_WARPS
+#define MVN_TC_MMA_WARPS 1
+#endif
+constexpr int kMmaWarps = MVN_TC_MMA_WARPS;
+constexpr int kThreadsTc = 32 * (kProdWarps + kConvWarps + kConsWarps + kMmaWarps);
 // layer 3 on the tensor core as well: D2[128 x 16] = h2[128 x 64] W3^T, K2 = 50 hidden units + bias column, padded
 // (N2 = max(16, n_states) output columns, so up to 64 states fit the slot's 64-column D regions)
 constexpr int kK2 = 64, kK2Steps = kK2 / 16;
@@ -108,6 +135,16 @@ __device__ __forceinline__ void static_for(F &&f) {
     }
 }
 __device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(addr), "r"(v[0]),
+                 "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]));
+}
+__device__ __forceinline__ void tmem_st4(uint32_t addr, const uint32_t *v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]));
+}
+__device__ __forceinline__ void tmem_st2(uint32_t addr, uint32_t v0, uint32_t v1) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v0), "r"(v1));
+}
+__device__ __forceinline__ void tmem_st8p(uint32_t addr, const uint32_t *v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(addr), "r"(v[0]),
                  "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]));
 }
@@ -208,15 +245,31 @@ __device__ __forceinline__ void recip4(u64 p, u64 q, u64 &rp, u64 &rq) {
     rq = mul2(inv, p);
 }
 // (g_k, g_{k+1}) -> fp16x2 words of the hi pieces and of the (unscaled) remainders (low half = even k)
+// (c0 + m h.lo, c1 + m h.hi) for a packed fp16 pair h and an fp16 constant m, one mixed-precision FMA (FHFMA) per value:
+// the fp16 piece goes back to fp32 inside the instruction (PTX ISA 8.6 fma.f32.f16), which saves the two unpack
+// instructions of a split.
+template <uint16_t M_BITS>
+__device__ __forceinline__ void fma_f32_f16x2(uint32_t h, float c0, float c1, float &r0, float &r1) {
+#if MVN_TC_MIXED_FMA
+    asm("{\n\t.reg .f16 lo, hi, m;\n\tmov.b32 {lo, hi}, %2;\n\tmov.b16 m, %5;\n\t"
+        "fma.rn.f32.f16 %0, lo, m, %3;\n\tfma.rn.f32.f16 %1, hi, m, %4;\n\t}\n"
+        : "=f"(r0), "=f"(r1)
+        : "r"(h), "f"(c0), "f"(c1), "n"(M_BITS));
+#else
+    // unpack (two HADD2.F32) + one packed FFMA2
+    const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&h));
+    const float m = __half2float(__ushort_as_half(M_BITS));
+    unpack2(fma2(pack2(f.x, f.y), pack2(m, m), pack2(c0, c1)), r0, r1);
+#endif
+}
 __device__ __forceinline__ void split2_pre(u64 g, uint32_t &whi, uint32_t &wlo) {
     float g0, g1;
     unpack2(g, g0, g1);
     const __half2 hi = __floats2half2_rn(g0, g1);
-    const float2 f = __half22float2(hi);
-    float r0, r1;
-    unpack2(fma2(pack2(f.x, f.y), 0xbf800000bf800000ull, g), r0, r1);   // g - f, exact
-    const __half2 lo = __floats2half2_rn(r0, r1);
     whi = *reinterpret_cast<const uint32_t *>(&hi);
+    float r0, r1;
+    fma_f32_f16x2<0xbc00>(whi, g0, g1, r0, r1);   // g - hi, exact
+    const __half2 lo = __floats2half2_rn(r0, r1);
     wlo = *reinterpret_cast<const uint32_t *>(&lo);
 }
 // X = 2048 a2 (converter warps, BEFORE the ReLU) -> fp16x2 words of the A operand of layer 3: hi = fp16(relu(a2)) rounded
@@ -234,37 +287,28 @@ __device__ __forceinline__ uint32_t cvt_f16x2_relu_rn(float hi_half, float lo_ha
     return d;
 }
 __device__ __forceinline__ void split2_relu(u64 X, uint32_t &whi, uint32_t &wlo) {
-    float h0, h1;
+    float h0, h1, x0, x1;
     unpack2(mul2(X, 0x3a0000003a000000ull), h0, h1);   // a2 = X / 2048
     whi = cvt_f16x2_relu_rz(h1, h0);                    // low half = even unit
-    const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&whi));
+    unpack2(X, x0, x1);
     float r0, r1;
-    unpack2(fma2(pack2(f.x, f.y), 0xc5000000c5000000ull, X), r0, r1);   // X - 2048 hi, exact
+    fma_f32_f16x2<0xe800>(whi, x0, x1, r0, r1);        // X - 2048 hi, exact
     wlo = cvt_f16x2_relu_rn(r1, r0);
 }
-// one k-step (16 hidden units = 8 TMEM columns) of this thread's frame: sigmoid -> split into registers
-template <bool LAST>
-__device__ __forceinline__ void compute_chunk(uint32_t sP_addr, int c0, u64 yy, uint32_t (&vh)[8], uint32_t (&vl)[8]) {
-#pragma unroll
-    for (int c = 0; c < 8; c += 2) {
-        if (!LAST || c < 2) {
-            u64 g0, g1;
-            recip4(denom2(sP_addr, 8 * c0 + c, yy), denom2(sP_addr, 8 * c0 + c + 1, yy), g0, g1);
-            split2_pre(g0, vh[c], vl[c]);
-            split2_pre(g1, vh[c + 1], vl[c + 1]);
-        } else {  // k = 100 is the bias column (2048 = fp16 0x6800 in the low half), k > 100 is zero padding
-            vh[c] = (c == 2) ? 0x00006800u : 0u;
-            vh[c + 1] = 0u;
-            vl[c] = vl[c + 1] = 0u;
-        }
-    }
+// one double-pair (4 hidden units = 2 TMEM columns per piece) of this thread's frame: sigmoid -> split into registers
+__device__ __forceinline__ void compute_dpair(uint32_t sP_addr, int dp, u64 yy, uint32_t *vh, uint32_t *vl) {
+    u64 g0, g1;
+    recip4(denom2(sP_addr, 2 * dp, yy), denom2(sP_addr, 2 * dp + 1, yy), g0, g1);
+    split2_pre(g0, vh[0], vl[0]);
+    split2_pre(g1, vh[1], vl[1]);
 }
 // converter warps: h2 = relu(D_main + D_corr / 2048) of this thread's frame, split into fp16 hi / scaled lo,
 // stored as the A operand of layer 3 (columns 0..31 of the slot's A_hi / A_lo regions, free after the MMAs of
 // layer 2); column k2 = 50 is the constant 1 that multiplies the b3 row of B2.
-template <bool DEC>
+template <int MODE>
 __device__ __forceinline__ void h2_to_tmem(uint32_t slot_lane) {
-    using LY = Lay<DEC>;
+    using LY = Lay<MODE>;
+    constexpr bool DEC = (MODE == 1);
 #pragma unroll
     for (int c0 = 0; c0 < kK2Steps; c0++) {   // 16 hidden units = 8 columns per step
         float m[16], c[16];
@@ -286,8 +330,8 @@ __device__ __forceinline__ void h2_to_tmem(uint32_t slot_lane) {
                 vl[q] = 0u;
             }
         }
-        tmem_st8(slot_lane + LY::Hh + c0 * 8, vh);
-        tmem_st8(slot_lane + LY::Hl + c0 * 8, vl);
+        tmem_st8(slot_lane + LY::hh(c0), vh);
+        tmem_st8(slot_lane + LY::hl(c0), vl);
     }
     asm volatile("tcgen05.wait::st.sync.aligned;");
 }
@@ -323,8 +367,10 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
     //         metrics of the 128 frames (128 KB) fill the shared memory, so this instance stages no tiles at all: the
     //         producers read their sample straight from global memory (one L1-resident line per frame and 32 stages),
     //         the consumers their targets.
-    constexpr bool DEC = (L <= 6);               // decoupled TMEM layout (tc::Lay): merged layer-2 accumulator, own h2 columns
-    using LY = tc::Lay<DEC>;
+    constexpr int LAYM = (L <= 6) ? MVN_TC_LAYOUT : 0;   // TMEM layout of a slot (tc::Lay)
+    constexpr bool DEC = (LAYM != 0);            // h2 outside the A columns: producers wait for the layer-2 MMAs, not the consumers
+    constexpr bool L2MERGED = (LAYM == 1);       // one layer-2 accumulator (scale-input-d)
+    using LY = tc::Lay<LAYM>;
     constexpr bool MERGED = (L >= 6);            // layer-3 correction chain folded into the main accumulator (64..128 columns)
     constexpr int NPASS = (L == 8) ? 2 : 1;      // layer-3 passes per stage
     constexpr int kQ = 4;                        // active TMEM lane quadrants = 32-frame warp tiles per CTA tile
@@ -336,8 +382,11 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
     constexpr uint32_t kLBO2 = (2 * N2 / 8) * 128;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint32_t tmem_base_s;
-    __shared__ __align__(8) uint64_t d_full[2], slot_free[2], a_full[2], d2_full[2];
-    constexpr int NT_TILES = DIRECT ? 0 : 4 * kQ;                                // producers (3 per quadrant) and consumers stage tiles
+    __shared__ __align__(8) uint64_t d_full[2], slot_free[2], a_full[4], d2_full[2];
+    // a_full: one barrier per issue warp (stage n -> a_full[n mod kAF], phase (n / kAF) & 1), so that every waiter sees every
+    // phase of its barrier (two warps alternating on one barrier could not tell phase u-1 from u+1)
+    constexpr uint32_t kAF = tc::kMmaWarps > 2 ? 4 : 2;
+    constexpr int NT_TILES = DIRECT ? 0 : (tc::kProdParts + 1) * kQ;             // producers and consumers stage tiles
     uint8_t *sB = smem_raw;                                                      // W2 pieces, hi rows | lo rows
     float *tiles = reinterpret_cast<float *>(smem_raw + tc::kBBytes);            // one 32x32 tile per such warp
     float *sP = tiles + NT_TILES * kTileFloats;                                  // [56][4] pair table for the packed sigmoid
@@ -345,10 +394,10 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, quad = warp & 3;
     const bool producer = warp < tc::kProdWarps;
     const bool converter = !producer && warp < tc::kProdWarps + tc::kConvWarps;
-    const bool mma_warp = warp == NW;
+    const bool mma_warp = warp >= NW;
     // tiles: one per producer warp (y) and one per consumer warp (targets); converters and the MMA warp use none
     const bool active = quad < kQ;
-    float *tile = tiles + (DIRECT ? 0 : (producer ? (warp >> 2) * kQ + (active ? quad : 0) : 3 * kQ + (active ? quad : 0)) * kTileFloats);
+    float *tile = tiles + (DIRECT ? 0 : (producer ? (warp >> 2) * kQ + (active ? quad : 0) : tc::kProdParts * kQ + (active ? quad : 0)) * kTileFloats);
 
     // ---- W2 (and b2 as column k=100) -> fp16 hi / scaled-lo pieces in the canonical K-major layout
     for (int idx = tid; idx < tc::kN * tc::kK; idx += tc::kThreadsTc) {
@@ -386,8 +435,10 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&d_full[s])));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&d2_full[s])));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&slot_free[s])), "n"(tc::kConsWarps));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&a_full[s])), "n"(tc::kProdWarps));
         }
+#pragma unroll
+        for (int s = 0; s < 4; s++)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&a_full[s])), "n"(tc::kProdWarps));
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     if (warp == 0) {
@@ -400,6 +451,21 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem = tmem_base_s;
     const uint32_t lane_base = uint32_t(quad * 32) << 16;
+    if (warp < 4) {
+        // constant columns of the layer-2 A operand, both slots: k = 100 multiplies the b2 row of B (2048 = fp16 0x6800 in the
+        // low half of column 50, the activations are pre-scaled by 2^11), k = 101..111 is zero padding.  Ordered before the
+        // first MMA by this warp's own first a_full arrival (wait::st + fence below).
+        const uint32_t z[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int sl = 0; sl < 2; sl++) {
+            const uint32_t base = tmem + sl * tc::kSlotCols + lane_base;
+            tc::tmem_st2(base + LY::Ah + 50, 0x00006800u, 0u);
+            tc::tmem_st4(base + LY::Ah + 52, z);
+            tc::tmem_st2(base + LY::Al + 50, 0u, 0u);
+            tc::tmem_st4(base + LY::Al + 52, z);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;");
+    }
     const uint32_t sB_addr = smem_addr(sB), sB2_addr = smem_addr(sB2);
     // D=F32, A=B=F16, both K-major, N>>3 at bit 17, M>>4 at bit 24; "w" = hi and lo pieces of B side by side
     constexpr uint32_t idesc2 = (1u << 4) | (uint32_t(N3 >> 3) << 17) | (uint32_t(tc::kM >> 4) << 24);
@@ -419,20 +485,20 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
         const uint32_t rows = uint32_t(half) * (N3 / 8) * 128;
 #pragma unroll
         for (int j = 0; j < tc::kK2Steps; j++)   // corr = h2_hi W3_lo
-            tc::mma_f16_ts(ts + tc::oDm, ts + LY::Hh + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2 + kLoRows + rows, kLBO2),
+            tc::mma_f16_ts(ts + tc::oDm, ts + LY::hh(j), tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2 + kLoRows + rows, kLBO2),
                            idesc2, j > 0);
 #pragma unroll
         for (int j = 0; j < tc::kK2Steps; j++)   // corr += h2_lo W3_hi
-            tc::mma_f16_ts(ts + tc::oDm, ts + LY::Hl + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2 + rows, kLBO2), idesc2, 1);
+            tc::mma_f16_ts(ts + tc::oDm, ts + LY::hl(j), tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2 + rows, kLBO2), idesc2, 1);
         // priors = h2_hi W3_hi + corr / 2048: the first MMA of the main chain reads D scaled by 2^-11
-        tc::mma_f16_ts_scale11(ts + tc::oDm, ts + LY::Hh, tc::b_desc(sB2_addr + rows, kLBO2), idesc2);
+        tc::mma_f16_ts_scale11(ts + tc::oDm, ts + LY::hh(0), tc::b_desc(sB2_addr + rows, kLBO2), idesc2);
 #pragma unroll
         for (int j = 1; j < tc::kK2Steps; j++)
-            tc::mma_f16_ts(ts + tc::oDm, ts + LY::Hh + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2 + rows, kLBO2), idesc2, 1);
+            tc::mma_f16_ts(ts + tc::oDm, ts + LY::hh(j), tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2 + rows, kLBO2), idesc2, 1);
     };
 
     if (producer) {
-        int rot = 0;  // which of the quadrant's three warps takes the seventh k-step in this stage
+        int rot = 0;  // which of the quadrant's producer warps takes the 25th double-pair in this stage
         for (int64_t ct = blockIdx.x; ct < n_cta_tiles; ct += gridDim.x) {
             const int64_t row0 = (ct * kQ + quad) * 32;
             for (int t0 = 0; t0 < p.T; t0 += 32) {
@@ -442,7 +508,7 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
                     for (int tt = 0; tt < t_end; tt++, n++) {
                         tc::mbar_wait<true>(smem_addr(&slot_free[n & 1]), ((n >> 1) & 1) ^ 1, timeout_flag);
                         __syncwarp();
-                        if (lane == 0) tc::mbar_arrive(smem_addr(&a_full[n & 1]));
+                        if (lane == 0) tc::mbar_arrive(smem_addr(&a_full[n % kAF]));
                         __syncwarp();
                     }
                     continue;
@@ -458,18 +524,18 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
                     // Compute this stage's pieces into registers BEFORE waiting for the slot: the sigmoid/split work
                     // then overlaps the MMAs and the consumer of the stage that still owns the slot.
                     TC_TRACE(0, tid == 0);
-                    TC_TRACE(28 + warp, lane == 0 && warp < 4);
-                    // k-steps per producer warp (three warps per TMEM lane quadrant): steps 0-1 | 2-3 | 4-5, 16 pairs of hidden
-                    // units each; the seventh step (pairs 48, 49 and the bias / padding columns) rotates among the three
-                    // warps from stage to stage, so that over three stages every warp computes 50 pairs (a fixed owner
-                    // made that warp the pace-setter of the whole CTA: pipeline trace)
-                    constexpr int NKS = 3;
-                    const int part = warp >> 2, c_base = 2 * part;
-                    const bool last_step = rot == part;
-                    uint32_t vh[NKS][8], vl[NKS][8];
+                    // Hidden units per producer warp (kProdParts warps per TMEM lane quadrant): the 50 pairs of units are 25
+                    // double-pairs (four sigmoids share one reciprocal); warp `part` owns double-pairs [DP part, DP part + DP)
+                    // = columns [2 DP part, ...) of A_hi / A_lo, and the 25th (columns 48, 49) rotates among the quadrant's
+                    // warps from stage to stage (a fixed owner made that warp the pace-setter of the whole CTA: pipeline
+                    // trace).  The bias column (50) and the zero padding (51..55) are written once per launch.
+                    constexpr int DP = 24 / tc::kProdParts, NC = 2 * DP;   // 8 double-pairs = 16 columns, or 6 = 12
+                    const int part = warp >> 2;
+                    const bool extra = rot == part;
+                    uint32_t vh[NC + 2], vl[NC + 2];
 #pragma unroll
-                    for (int i = 0; i < 2; i++) tc::compute_chunk<false>(sP_addr, c_base + i, yy, vh[i], vl[i]);
-                    if (last_step) tc::compute_chunk<true>(sP_addr, 6, yy, vh[2], vl[2]);
+                    for (int i = 0; i < DP; i++) tc::compute_dpair(sP_addr, DP * part + i, yy, vh + 2 * i, vl + 2 * i);
+                    if (extra) tc::compute_dpair(sP_addr, 24, yy, vh + NC, vl + NC);
                     TC_TRACE(1, tid == 0);
                     // (128 / 256 states are bound by the consumers: there the producers park instead of polling, which
                     //  would take issue slots from the consumer warp on their scheduler)
@@ -478,22 +544,29 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
                     tc::mbar_wait<(MVN_PROD_PARK || L >= 7)>(smem_addr(DEC ? &d_full[slot] : &slot_free[slot]), (use & 1) ^ 1, timeout_flag);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     TC_TRACE(2, tid == 0);
-#pragma unroll
-                    for (int i = 0; i < 2; i++) {
-                        tc::tmem_st8(slot_lane + LY::Ah + (c_base + i) * 8, vh[i]);
-                        tc::tmem_st8(slot_lane + LY::Al + (c_base + i) * 8, vl[i]);
+                    {
+                        const uint32_t ah = slot_lane + LY::Ah + NC * part, al = slot_lane + LY::Al + NC * part;
+                        tc::tmem_st8p(ah, vh);
+                        tc::tmem_st8p(al, vl);
+                        if constexpr (NC == 16) {
+                            tc::tmem_st8p(ah + 8, vh + 8);
+                            tc::tmem_st8p(al + 8, vl + 8);
+                        } else {
+                            tc::tmem_st4(ah + 8, vh + 8);
+                            tc::tmem_st4(al + 8, vl + 8);
+                        }
+                        if (extra) {
+                            tc::tmem_st2(slot_lane + LY::Ah + 48, vh[NC], vh[NC + 1]);
+                            tc::tmem_st2(slot_lane + LY::Al + 48, vl[NC], vl[NC + 1]);
+                        }
                     }
-                    if (last_step) {
-                        tc::tmem_st8(slot_lane + LY::Ah + 6 * 8, vh[2]);
-                        tc::tmem_st8(slot_lane + LY::Al + 6 * 8, vl[2]);
-                    }
-                    rot = rot == 2 ? 0 : rot + 1;
+                    rot = rot == tc::kProdParts - 1 ? 0 : rot + 1;
                     asm volatile("tcgen05.wait::st.sync.aligned;");
                     asm volatile("tcgen05.fence::before_thread_sync;");
                     TC_TRACE(3, tid == 0);
                     TC_TRACE(16 + warp, lane == 0);
                     __syncwarp();
-                    if (lane == 0) tc::mbar_arrive(smem_addr(&a_full[slot]));  // one arrival per producer warp
+                    if (lane == 0) tc::mbar_arrive(smem_addr(&a_full[n % kAF]));  // one arrival per producer warp
                     __syncwarp();
                 }
                 __syncwarp();
@@ -506,17 +579,19 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
                 const int t_end = min(32, p.n_stages - t0);
 #pragma unroll 1
                 for (int tt = 0; tt < t_end; tt++, n++) {
+                    if (tc::kMmaWarps > 1 && int(n % tc::kMmaWarps) != warp - NW) continue;   // another issue warp's stage
                     const uint32_t slot = n & 1, use = n >> 1;
-                    tc::mbar_wait(smem_addr(&a_full[slot]), use & 1, timeout_flag);
+                    tc::mbar_wait(smem_addr(&a_full[n % kAF]), (n / kAF) & 1, timeout_flag);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     TC_TRACE(4, lane == 0);
                     if constexpr (DEC) {   // the accumulator columns also carry the priors of the slot's previous use: wait for its consumers
                         tc::mbar_wait(smem_addr(&slot_free[slot]), (use & 1) ^ 1, timeout_flag);
                         asm volatile("tcgen05.fence::after_thread_sync;");
                     }
+                    TC_TRACE(15, lane == 0);
                     if (tc::elect_one()) {
                         const uint32_t ts = tmem + slot * tc::kSlotCols;
-                        if constexpr (!DEC) {
+                        if constexpr (!L2MERGED) {
 #pragma unroll
                             for (int j = 0; j < tc::kKSteps; j++)   // D_main | D_corr = A_hi [B_hi | B_lo]
                                 tc::mma_f16_ts(ts + tc::oDm, ts + LY::Ah + j * 8, tc::b_desc(sB_addr + uint32_t(2 * j) * tc::kLBO), idescw,
@@ -561,21 +636,21 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
                     tc::mbar_wait<MVN_CONS_PARK>(smem_addr(&d_full[slot]), use & 1, timeout_flag);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     TC_TRACE(7, warp == tc::kProdWarps && lane == 0);
-                    if (active) tc::h2_to_tmem<DEC>(slot_lane);
+                    if (active) tc::h2_to_tmem<LAYM>(slot_lane);
                     asm volatile("tcgen05.fence::before_thread_sync;");
                     TC_TRACE(8, warp == tc::kProdWarps && lane == 0);
                     asm volatile("bar.sync 2, %0;" ::"n"(32 * tc::kConvWarps));
                     TC_TRACE(9, warp == tc::kProdWarps && lane == 0);
-                    if (warp == tc::kProdWarps + 1 && tc::elect_one()) {  // one thread (not on the MMA warp's scheduler) issues layer 3
+                    if (warp == tc::kProdWarps + (tc::kMmaWarps > 1 ? int((n + 2) & 3) : 1) && tc::elect_one()) {  // one thread issues layer 3
                         asm volatile("tcgen05.fence::after_thread_sync;");
                         if constexpr (!MERGED) {   // 4 + 4 MMAs
 #pragma unroll
                             for (int j = 0; j < tc::kK2Steps; j++)   // priors_main | priors_corr = h2_hi [W3_hi | W3_lo]
-                                tc::mma_f16_ts(ts + tc::oDm, ts + LY::Hh + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2, kLBO2),
+                                tc::mma_f16_ts(ts + tc::oDm, ts + LY::hh(j), tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2, kLBO2),
                                                idesc2w, j > 0);
 #pragma unroll
                             for (int j = 0; j < tc::kK2Steps; j++)   // priors_corr += h2_lo W3_hi
-                                tc::mma_f16_ts(ts + tc::oDm + N2, ts + LY::Hl + j * 8, tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2, kLBO2),
+                                tc::mma_f16_ts(ts + tc::oDm + N2, ts + LY::hl(j), tc::b_desc(sB2_addr + uint32_t(2 * j) * kLBO2, kLBO2),
                                                idesc2, 1);
                         } else {                   // 4 + 4 + 4 MMAs of N = 128 into one accumulator (pass 0: states 0..127)
                             issue_layer3_merged(ts, 0);
@@ -725,7 +800,7 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
 template <int L>
 constexpr size_t tc_smem_bytes() {   // + the consumers' survivor masks in MLSE mode (launch_tc)
     constexpr int kQ = 4;
-    return size_t(tc::kBBytes) + tc::b2_bytes(1 << L) + (size_t(L == 8 ? 0 : 4 * kQ) * kTileFloats + 4 * (tc::kK / 2)) * sizeof(float) +
+    return size_t(tc::kBBytes) + tc::b2_bytes(1 << L) + (size_t(L == 8 ? 0 : (tc::kProdParts + 1) * kQ) * kTileFloats + 4 * (tc::kK / 2)) * sizeof(float) +
            (L > 5 ? SmemTrellis<L>::bytes(32 * kQ) : 0);
 }
 

@@ -11,7 +11,7 @@ import torch
 import bench
 from meta_viterbinet_b200 import _lib
 
-_lib.LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libmvn_trace.so')
+_lib.LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libmvn_trace.so')   # nvcc <build.py flags> -DMVN_TC_TRACE
 import meta_viterbinet_b200 as mvn
 
 dev = torch.device('cuda', 0)
@@ -33,13 +33,15 @@ for s in range(8, 24):
 d = lambda a, b: float(np.median(t[16:56, b] - t[16:56, a]))
 print('\nmedian segment lengths (cycles), stages 16..55:')
 for a, b, label in [(0, 1, 'producer compute'), (1, 2, 'producer waits for slot'), (2, 3, 'producer tcgen05.st + wait::st'),
-                    (3, 4, 'a_full arrive -> MMA warp wakes'), (4, 5, 'MMA warp issues 21 MMAs'), (5, 7, 'commit -> consumer sees d_full'),
-                    (7, 8, 'consumer: ld D, relu, split, st A2'), (8, 9, 'consumer barrier'), (9, 10, 'issue 12 layer-3 MMAs'),
-                    (10, 11, 'layer-3 MMAs -> d2_full seen'), (11, 12, 'ld priors, release slot'), (12, 13, 'ACS'), (6, 7, 'consumer idle waiting for d_full')]:
+                    (3, 4, 'a_full arrive -> MMA warp wakes'), (4, 15, 'MMA warp waits for slot_free (consumers)'),
+                    (15, 5, 'MMA warp issues the layer-2 MMAs'), (5, 7, 'commit -> converter sees d_full'),
+                    (7, 8, 'converter: ld D, relu, split, st h2'), (8, 9, 'converter barrier'), (9, 10, 'issue the layer-3 MMAs'),
+                    (10, 11, 'layer-3 issued -> consumer sees d2_full'), (11, 12, 'consumer: ld priors, release slot'), (12, 13, 'ACS'),
+                    (6, 7, 'converter idle waiting for d_full')]:
     print(f'  {label:40s} {d(a, b):8.0f}')
+print(f'  d_full seen (slot use k) -> d_full seen (use k+1), same slot: {float(np.median(t[18:56, 7] - t[16:54, 7])):8.0f}')
 print(f'  stage period (consumer)                  {float(np.median(np.diff(t[16:56, 13]))):8.0f}')
 mhz = (t[60, 0] - t[4, 0]) / max(1, (t[60, 14] - t[4, 14])) * 1000.0
 print(f'  effective SM clock during the kernel (clock64 / globaltimer over stages 4..60): {mhz:8.0f} MHz')
 print('  A operand stored, per producer warp relative to warp 0 (median over stages 16..55, cycles); warps w, w+4, w+8 share a quadrant:')
-print('    ' + ' '.join(f'{float(np.median(t[16:56, 16 + w] - t[16:56, 16])):6.0f}' for w in range(12)))
-print('  start -> stored, producer warps 0..3: ' + ' '.join(f'{float(np.median(t[16:56, 16 + w] - t[16:56, 28 + w])):6.0f}' for w in range(4)))
+print('    ' + ' '.join(f'{float(np.median(t[16:56, 16 + w] - t[16:56, 16])):6.0f}' for w in range(12 if t[20, 31] == 0 else 16)))
