@@ -44,6 +44,9 @@ namespace mvn {
 #ifndef MVN_TC_MIXED_FMA
 #define MVN_TC_MIXED_FMA 0   // FHFMA (fma.f32.f16) in the hi/lo splits: one instruction less per pair, but measured 3 % SLOWER (L=4 17.1 -> 16.5 G sym/s)
 #endif
+#ifndef MVN_TC_EXPERIMENT
+#define MVN_TC_EXPERIMENT 0   // 1, 2: bound-finding builds of the producers, never shipped
+#endif
 #ifndef MVN_CONS_PARK
 #define MVN_CONS_PARK true
 #endif
@@ -233,13 +236,23 @@ __device__ __forceinline__ u64 denom2(uint32_t sP_addr, int pair, u64 yy) {
     lds128(sP_addr + 16 * pair, w, b);
     float x0, x1;
     unpack2(fma2(yy, w, b), x0, x1);
+#if MVN_TC_EXPERIMENT == 3   // bound-finding build (no overflow guard): no FMNMX clamps
+    return add2(pack2(ex2_approx(x0), ex2_approx(x1)), 0x3a0000003a000000ull);
+#elif MVN_TC_EXPERIMENT == 2   // bound-finding build (wrong results): no MUFU.EX2
+    return add2(pack2(fminf(x0, 30.f) + 1.5f, fminf(x1, 30.f) + 1.5f), 0x3a0000003a000000ull);
+#else
     return add2(pack2(ex2_approx(fminf(x0, 30.f)), ex2_approx(fminf(x1, 30.f))), 0x3a0000003a000000ull);  // + 2^-11
+#endif
 }
 // (1/p.x, 1/p.y) and (1/q.x, 1/q.y) from one reciprocal
 __device__ __forceinline__ void recip4(u64 p, u64 q, u64 &rp, u64 &rq) {
     float m0, m1;
     unpack2(mul2(p, q), m0, m1);                   // (p.x q.x, p.y q.y)
+#if MVN_TC_EXPERIMENT == 1   // bound-finding build (wrong results): no MUFU.RCP
+    const float r = m0 * m1 + 3.f;
+#else
     const float r = rcp_approx(m0 * m1);
+#endif
     const u64 inv = pack2(r * m1, r * m0);         // (1 / (p.x q.x), 1 / (p.y q.y))
     rp = mul2(inv, q);
     rq = mul2(inv, p);
@@ -534,7 +547,12 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
                     const bool extra = rot == part;
                     uint32_t vh[NC + 2], vl[NC + 2];
 #pragma unroll
-                    for (int i = 0; i < DP; i++) tc::compute_dpair(sP_addr, DP * part + i, yy, vh + 2 * i, vl + 2 * i);
+                    for (int i = 0; i < DP; i++) {
+#if MVN_TC_EXPERIMENT == 4   // bound-finding build (wrong results): half of the sigmoids
+                        if (i & 1) { vh[2 * i] = vh[2 * i - 2]; vh[2 * i + 1] = vh[2 * i - 1]; vl[2 * i] = vl[2 * i - 2]; vl[2 * i + 1] = vl[2 * i - 1]; continue; }
+#endif
+                        tc::compute_dpair(sP_addr, DP * part + i, yy, vh + 2 * i, vl + 2 * i);
+                    }
                     if (extra) tc::compute_dpair(sP_addr, 24, yy, vh + NC, vl + NC);
                     TC_TRACE(1, tid == 0);
                     // (128 / 256 states are bound by the consumers: there the producers park instead of polling, which
