@@ -560,6 +560,7 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
                     // DEC: the A columns are free once the layer-2 MMAs of the slot's previous use have read them (d_full);
                     // round-1 layout: once the consumers have released the slot (h2 lives in the A columns)
                     tc::mbar_wait<(MVN_PROD_PARK || L >= 7)>(smem_addr(DEC ? &d_full[slot] : &slot_free[slot]), (use & 1) ^ 1, timeout_flag);
+                    TC_TRACE(28, tid == 0);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     TC_TRACE(2, tid == 0);
                     {
@@ -579,13 +580,16 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
                         }
                     }
                     rot = rot == tc::kProdParts - 1 ? 0 : rot + 1;
+                    TC_TRACE(29, tid == 0);
                     asm volatile("tcgen05.wait::st.sync.aligned;");
+                    TC_TRACE(30, tid == 0);
                     asm volatile("tcgen05.fence::before_thread_sync;");
                     TC_TRACE(3, tid == 0);
                     TC_TRACE(16 + warp, lane == 0);
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(smem_addr(&a_full[n % kAF]));  // one arrival per producer warp
                     __syncwarp();
+                    TC_TRACE(31, tid == 0);
                 }
                 __syncwarp();
             }
