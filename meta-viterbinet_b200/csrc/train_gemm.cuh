@@ -1,7 +1,7 @@
 // Batched (meta-)training step of the priors net as a sequence of small register-tiled GEMMs out of shared memory
 // (a9-a11: trainers/trainer.py:425-453 meta_train_loop, :492-505 run_train_loop, metavnet_trainer.py:41-50 loss).
 //
-// One CTA (256 threads) owns one realisation.  Everything of a step lives in shared memory:
+// One CTA (MVN_TRAIN_THREADS = 512 threads) owns one realisation.  Everything of a step lives in shared memory:
 //   Wset   the weights in a padded torch layout  [w1 100][b1 100][W2 52x100][b2 52][W3 SPx52][b3 SP]   (rows 50, 51 of
 //          W2 / b2 and columns 50, 51 of W3 are zero, SP = max(S, 4))
 //   Vset   the tangent direction in the same layout (MAML's Hessian-vector product only)

@@ -327,7 +327,7 @@ int tc_timeout_seen() {
 __device__ long long g_tc_trace[64 * 32];
 #endif
 
-// tcgen05 variant (memory_length <= 6): every CTA stages its own weights (W2/b2 as bf16 pieces, the rest fp32).
+// tcgen05 variant (memory_length 1..8): every CTA stages its own weights (W2/b2 and W3/b3 as fp16 pieces in shared memory).
 template <int L, bool MLSE>
 static int launch_tc_mode(VnetParams p, cudaStream_t st) {
     size_t smem = tc_smem_bytes<L>();
@@ -369,7 +369,7 @@ static int launch_tc_mode(VnetParams p, cudaStream_t st) {
     return MVN_OK;
 }
 
-// tcgen05 variant (memory_length <= 6): every CTA stages its own weights (W2/b2 as fp16 pieces, the rest fp32).
+// reference decision rule for every L; the fused traceback (MLSE) instance is built for memory_length <= 6
 template <int L>
 static int launch_tc(const VnetParams &p, cudaStream_t st) {
     if (p.decision == MVN_DECIDE_REFERENCE) return launch_tc_mode<L, false>(p, st);

@@ -371,7 +371,8 @@ __device__ __forceinline__ void h2_to_tmem(uint32_t slot_lane) {
 template <int L, bool MLSE>
 __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch timeout_flag, long long *trace) {
     static_assert(L <= 8, "tcgen05 variant: memory_length 1..8");
-    // L <= 6: priors_main | priors_corr side by side in the slot's two 64-column D regions (one N = 2 N2 MMA per k-step).
+    // L <= 5: priors_main | priors_corr side by side inside the slot's 64 accumulator columns (one N = 2 N2 MMA per k-step).
+    // L == 6: 64 priors: the correction chain is folded into the main chain (scale-input-d), as for L == 7.
     // L == 7: 128 priors fill both regions, so the correction chain is computed first and folded into the main chain by
     //         the tensor core itself (scale-input-d: D = A B + D 2^-11): ONE 128-column accumulator.
     // L == 8: 256 priors go through the same 128 columns in TWO layer-3 passes per stage (states 0..127, then 128..255:
