@@ -44,6 +44,9 @@ namespace mvn {
 #ifndef MVN_TC_MIXED_FMA
 #define MVN_TC_MIXED_FMA 0   // FHFMA (fma.f32.f16) in the hi/lo splits: one instruction less per pair, but measured 3 % SLOWER (L=4 17.1 -> 16.5 G sym/s)
 #endif
+#ifndef MVN_TC_EARLY_PROBE
+#define MVN_TC_EARLY_PROBE 1
+#endif
 #ifndef MVN_TC_EXPERIMENT
 #define MVN_TC_EXPERIMENT 0   // 1, 2: bound-finding builds of the producers, never shipped
 #endif
@@ -151,6 +154,12 @@ __device__ __forceinline__ void tmem_st8p(uint32_t addr, const uint32_t *v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(addr), "r"(v[0]),
                  "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]));
 }
+__device__ __forceinline__ void tmem_st16p(uint32_t addr, const uint32_t *v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(addr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+        "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]));
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t addr, float *r) {
     uint32_t u[16];
     asm volatile(
@@ -208,6 +217,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, TcWatch
             }
         }
     }
+}
+// non-blocking probe of a phase (true = complete)
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(done)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    return done != 0;
 }
 // One thread of a converged warp.  The compiler recognises the elect.sync predicate as "a single thread": MMA
 // operands then go to uniform registers once, instead of the per-instruction ELECT / R2UR / BRA.U.ANY loop it emits
@@ -548,10 +566,15 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
                     const bool extra = rot == part;
                     uint32_t vh[NC + 2], vl[NC + 2];
 #pragma unroll
+                    // The slot's barrier is probed in the MIDDLE of the stage's arithmetic: at its end the probe would queue
+                    // behind this scheduler's MUFU backlog (pipeline trace: 270 cycles for a wait that succeeds at once).
+                    const uint32_t slot_bar = smem_addr(DEC ? &d_full[slot] : &slot_free[slot]);
+                    bool slot_ready = false;
                     for (int i = 0; i < DP; i++) {
 #if MVN_TC_EXPERIMENT == 4   // bound-finding build (wrong results): half of the sigmoids
                         if (i & 1) { vh[2 * i] = vh[2 * i - 2]; vh[2 * i + 1] = vh[2 * i - 1]; vl[2 * i] = vl[2 * i - 2]; vl[2 * i + 1] = vl[2 * i - 1]; continue; }
 #endif
+                        if (MVN_TC_EARLY_PROBE && i == DP / 2) slot_ready = tc::mbar_test(slot_bar, (use & 1) ^ 1);
                         tc::compute_dpair(sP_addr, DP * part + i, yy, vh + 2 * i, vl + 2 * i);
                     }
                     if (extra) tc::compute_dpair(sP_addr, 24, yy, vh + NC, vl + NC);
@@ -560,18 +583,18 @@ __global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch 
                     //  would take issue slots from the consumer warp on their scheduler)
                     // DEC: the A columns are free once the layer-2 MMAs of the slot's previous use have read them (d_full);
                     // round-1 layout: once the consumers have released the slot (h2 lives in the A columns)
-                    tc::mbar_wait<(MVN_PROD_PARK || L >= 7)>(smem_addr(DEC ? &d_full[slot] : &slot_free[slot]), (use & 1) ^ 1, timeout_flag);
+                    if (!slot_ready) tc::mbar_wait<(MVN_PROD_PARK || L >= 7)>(slot_bar, (use & 1) ^ 1, timeout_flag);
                     TC_TRACE(28, tid == 0);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     TC_TRACE(2, tid == 0);
                     {
                         const uint32_t ah = slot_lane + LY::Ah + NC * part, al = slot_lane + LY::Al + NC * part;
-                        tc::tmem_st8p(ah, vh);
-                        tc::tmem_st8p(al, vl);
                         if constexpr (NC == 16) {
-                            tc::tmem_st8p(ah + 8, vh + 8);
-                            tc::tmem_st8p(al + 8, vl + 8);
+                            tc::tmem_st16p(ah, vh);
+                            tc::tmem_st16p(al, vl);
                         } else {
+                            tc::tmem_st8p(ah, vh);
+                            tc::tmem_st8p(al, vl);
                             tc::tmem_st4(ah + 8, vh + 8);
                             tc::tmem_st4(al + 8, vl + 8);
                         }
