@@ -19,12 +19,12 @@
 //  12 producer warps : y -> 100 sigmoids -> fp16 hi/lo split -> tcgen05.st  A_hi, A_lo [128 x 112] (2 x 56 columns)
 //                      (three warps per TMEM lane quadrant serve the same 32 frames and split the hidden units; the
 //                       bias / padding columns are written once per launch)
-//   1 MMA warp       : the layer-2 tcgen05.mma.kind::f16 of a stage (M=128, K=16, N=64: A_hi x W2_lo, A_hi x W2_hi with
+//   4 MMA warps      : (one per scheduler, taking the stages round-robin) the layer-2 tcgen05.mma.kind::f16 of a stage (M=128, K=16, N=64: A_hi x W2_lo, A_hi x W2_hi with
 //                      scale-input-d, A_lo x W2_hi = 21 MMAs; L >= 7: 7 of N=128 + 7 of N=64 into D_main | D_corr),
 //                      A from TMEM, B from shared memory in the canonical K-major no-swizzle layout; tcgen05.commit -> d_full
 //   4 converter warps: tcgen05.ld of the layer-2 result -> ReLU -> the same hi/lo split -> tcgen05.st as the A operand
 //                      of LAYER 3, which also runs on the tensor core (8-12 MMAs, W3 pieces and b3 in shared memory,
-//                      issued by one converter thread; 256 states: two passes)
+//                      issued by one converter thread, the four warps taking turns; 256 states: two passes)
 //   4 consumer warps : tcgen05.ld of the priors -> ACS on the frame's private path metrics, decision bit (or survivor
 //                      masks + in-kernel traceback), outputs, BER.  Converters and consumers pipeline across the two
 //                      slots: stage n+1 is converted while layer 3 of stage n runs and its ACS is done.
@@ -98,7 +98,7 @@ static_assert(kProdWarps == 12 || kProdWarps == 16, "24 double-pairs of hidden u
 // the same share of tcgen05.mma issue.  With ONE issue warp the pipeline trace showed the three producer warps on its
 // scheduler a full stage behind the other nine: a tcgen05.mma waiting for the tensor pipe holds up its scheduler.
 #ifndef MVN_TC_MMA_WARPS
-#define MVN_TC_MMA_WARPS 1
+#define MVN_TC_MMA_WARPS 4   // 1: L=4 17.4, 4: 17.8 G sym/s (once the producers' barrier probe was off the critical path; before that 17.10 vs 17.13)
 #endif
 constexpr int kMmaWarps = MVN_TC_MMA_WARPS;
 constexpr int kThreadsTc = 32 * (kProdWarps + kConvWarps + kConsWarps + kMmaWarps);
@@ -387,7 +387,7 @@ __device__ __forceinline__ void h2_to_tmem(uint32_t slot_lane) {
 #endif
 
 template <int L, bool MLSE>
-__global__ void __maxnreg__(80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch timeout_flag, long long *trace) {
+__global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch timeout_flag, long long *trace) {
     static_assert(L <= 8, "tcgen05 variant: memory_length 1..8");
     // L <= 5: priors_main | priors_corr side by side inside the slot's 64 accumulator columns (one N = 2 N2 MMA per k-step).
     // L == 6: 64 priors: the correction chain is folded into the main chain (scale-input-d), as for L == 7.
