@@ -47,6 +47,9 @@ namespace mvn {
 #ifndef MVN_TC_EARLY_PROBE
 #define MVN_TC_EARLY_PROBE 1
 #endif
+#ifndef MVN_TC_LATE_PUBLISH
+#define MVN_TC_LATE_PUBLISH 1
+#endif
 #ifndef MVN_TC_EXPERIMENT
 #define MVN_TC_EXPERIMENT 0   // 1, 2: bound-finding builds of the producers, never shipped
 #endif
@@ -531,6 +534,18 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
 
     if (producer) {
         int rot = 0;  // which of the quadrant's producer warps takes the 25th double-pair in this stage
+        // MVN_TC_LATE_PUBLISH: the tcgen05.st of stage n are published (wait::st, fence, a_full arrival) after the first
+        // double-pair of stage n+1 has been computed into spare registers, so their latency overlaps arithmetic
+        bool pending = false;
+        uint32_t pending_n = 0;
+        auto publish = [&]() {
+            asm volatile("tcgen05.wait::st.sync.aligned;");
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(smem_addr(&a_full[pending_n % kAF]));  // one arrival per producer warp
+            __syncwarp();
+            pending = false;
+        };
         for (int64_t ct = blockIdx.x; ct < n_cta_tiles; ct += gridDim.x) {
             const int64_t row0 = (ct * kQ + quad) * 32;
             for (int t0 = 0; t0 < p.T; t0 += 32) {
@@ -545,6 +560,7 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
                     }
                     continue;
                 }
+                if (pending) publish();   // not behind the global loads of the next tile
                 if constexpr (!DIRECT) warp_load_tile(p.y, p.B, p.T, p.T, row0, t0, tile, lane, vec_in);
                 const float *yrow = p.y + (row0 + lane < p.B ? row0 + lane : 0) * int64_t(p.T) + t0;
 #pragma unroll 1
@@ -575,6 +591,13 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
                         if (i & 1) { vh[2 * i] = vh[2 * i - 2]; vh[2 * i + 1] = vh[2 * i - 1]; vl[2 * i] = vl[2 * i - 2]; vl[2 * i + 1] = vl[2 * i - 1]; continue; }
 #endif
                         if (MVN_TC_EARLY_PROBE && i == DP / 2) slot_ready = tc::mbar_test(slot_bar, (use & 1) ^ 1);
+                        if (MVN_TC_LATE_PUBLISH && i == 0) {
+                            uint32_t th[2], tl[2];   // vh / vl may still be read by the stores of the previous stage
+                            tc::compute_dpair(sP_addr, DP * part, yy, th, tl);
+                            if (pending) publish();
+                            vh[0] = th[0], vh[1] = th[1], vl[0] = tl[0], vl[1] = tl[1];
+                            continue;
+                        }
                         tc::compute_dpair(sP_addr, DP * part + i, yy, vh + 2 * i, vl + 2 * i);
                     }
                     if (extra) tc::compute_dpair(sP_addr, 24, yy, vh + NC, vl + NC);
@@ -605,19 +628,27 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
                     }
                     rot = rot == tc::kProdParts - 1 ? 0 : rot + 1;
                     TC_TRACE(29, tid == 0);
-                    asm volatile("tcgen05.wait::st.sync.aligned;");
-                    TC_TRACE(30, tid == 0);
-                    asm volatile("tcgen05.fence::before_thread_sync;");
-                    TC_TRACE(3, tid == 0);
-                    TC_TRACE(16 + warp, lane == 0);
-                    __syncwarp();
-                    if (lane == 0) tc::mbar_arrive(smem_addr(&a_full[n % kAF]));  // one arrival per producer warp
-                    __syncwarp();
-                    TC_TRACE(31, tid == 0);
+                    if constexpr (MVN_TC_LATE_PUBLISH) {
+                        pending = true;
+                        pending_n = n;
+                        TC_TRACE(3, tid == 0);            // (stores issued; published during the next stage)
+                        TC_TRACE(16 + warp, lane == 0);
+                    } else {
+                        asm volatile("tcgen05.wait::st.sync.aligned;");
+                        TC_TRACE(30, tid == 0);
+                        asm volatile("tcgen05.fence::before_thread_sync;");
+                        TC_TRACE(3, tid == 0);
+                        TC_TRACE(16 + warp, lane == 0);
+                        __syncwarp();
+                        if (lane == 0) tc::mbar_arrive(smem_addr(&a_full[n % kAF]));  // one arrival per producer warp
+                        __syncwarp();
+                        TC_TRACE(31, tid == 0);
+                    }
                 }
                 __syncwarp();
             }
         }
+        if (pending) publish();
     } else if (mma_warp) {
         // one warp does nothing but issue: per stage 7 + 7 MMAs, then tcgen05.commit -> d_full[slot]
         for (int64_t ct = blockIdx.x; ct < n_cta_tiles; ct += gridDim.x) {

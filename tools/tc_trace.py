@@ -32,16 +32,17 @@ for s in range(8, 24):
     print(f'{s:5d} ' + ' '.join(f'{int(t[s, e] - base):13d}' for e in range(14)))
 d = lambda a, b: float(np.median(t[16:56, b] - t[16:56, a]))
 print('\nmedian segment lengths (cycles), stages 16..55:')
-for a, b, label in [(0, 1, 'producer compute'), (1, 2, 'producer waits for slot'), (2, 3, 'producer tcgen05.st + wait::st'),
+for a, b, label in [(0, 1, 'producer compute'), (1, 2, 'producer waits for slot'), (2, 3, 'producer tcgen05.st (+ wait::st unless late publish)'),
                     (3, 4, 'a_full arrive -> MMA warp wakes'), (4, 15, 'MMA warp waits for slot_free (consumers)'),
                     (15, 5, 'MMA warp issues the layer-2 MMAs'), (5, 7, 'commit -> converter sees d_full'),
                     (7, 8, 'converter: ld D, relu, split, st h2'), (8, 9, 'converter barrier'), (9, 10, 'issue the layer-3 MMAs'),
                     (10, 11, 'layer-3 issued -> consumer sees d2_full'), (11, 12, 'consumer: ld priors, release slot'), (12, 13, 'ACS'),
                     (6, 7, 'converter idle waiting for d_full')]:
     print(f'  {label:40s} {d(a, b):8.0f}')
-print('  producer warp 0 tail: computed -> try_wait done -> fence -> st issued -> wait::st done -> fence -> arrived -> next start')
-print('    ' + ' '.join(f'{float(np.median(t[16:56, b] - t[16:56, a])):6.0f}' for a, b in [(1, 28), (28, 2), (2, 29), (29, 30), (30, 3), (3, 31)])
-      + f' {float(np.median(t[17:57, 0] - t[16:56, 31])):6.0f}')
+late = t[20, 30] == 0   # MVN_TC_LATE_PUBLISH: wait::st / fence / arrive happen inside the next stage
+print('  producer warp 0 tail: computed -> try_wait done -> fence -> st issued' + (' -> next start (late publish)' if late else ' -> wait::st done -> fence -> arrived -> next start'))
+print('    ' + ' '.join(f'{float(np.median(t[16:56, b] - t[16:56, a])):6.0f}' for a, b in ([(1, 28), (28, 2), (2, 29)] if late else [(1, 28), (28, 2), (2, 29), (29, 30), (30, 3), (3, 31)]))
+      + f' {float(np.median(t[17:57, 0] - t[16:56, 29 if late else 31])):6.0f}')
 print(f'  d_full seen (slot use k) -> d_full seen (use k+1), same slot: {float(np.median(t[18:56, 7] - t[16:54, 7])):8.0f}')
 print(f'  stage period (consumer)                  {float(np.median(np.diff(t[16:56, 13]))):8.0f}')
 mhz = (t[60, 0] - t[4, 0]) / max(1, (t[60, 14] - t[4, 14])) * 1000.0
