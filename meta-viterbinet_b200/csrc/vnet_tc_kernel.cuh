@@ -50,6 +50,9 @@ namespace mvn {
 #ifndef MVN_TC_LATE_PUBLISH
 #define MVN_TC_LATE_PUBLISH 1
 #endif
+#ifndef MVN_TC_CLAMP_FREE
+#define MVN_TC_CLAMP_FREE 0   // clamp-free producer path behind a per-stage |y| vote: L=4 17.6 vs 18.0 G sym/s (second copy of the stage body, spills)
+#endif
 #ifndef MVN_TC_EXPERIMENT
 #define MVN_TC_EXPERIMENT 0   // 1, 2: bound-finding builds of the producers, never shipped
 #endif
@@ -252,11 +255,14 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // profiles/): EX2 + RCP per unit is 200 MUFU per symbol.  Four reciprocals share ONE MUFU.RCP (Montgomery's trick:
 // 1/a = b c d / (a b c d), arranged on packed pairs so that it costs 7 instructions per four values); the exponent
 // is clamped so that the product of four d' stays finite (sigmoid floor 2^-41, far below fp32 resolution of the sums).
+template <bool CLAMP = true>
 __device__ __forceinline__ u64 denom2(uint32_t sP_addr, int pair, u64 yy) {
     u64 w, b;
     lds128(sP_addr + 16 * pair, w, b);
     float x0, x1;
     unpack2(fma2(yy, w, b), x0, x1);
+    // CLAMP = false: the caller has checked |y| against the launch's safe bound (every exponent <= 29.5), same bits
+    if (!CLAMP) return add2(pack2(ex2_approx(x0), ex2_approx(x1)), 0x3a0000003a000000ull);
 #if MVN_TC_EXPERIMENT == 3   // bound-finding build (no overflow guard): no FMNMX clamps
     return add2(pack2(ex2_approx(x0), ex2_approx(x1)), 0x3a0000003a000000ull);
 #elif MVN_TC_EXPERIMENT == 2   // bound-finding build (wrong results): no MUFU.EX2
@@ -330,9 +336,10 @@ __device__ __forceinline__ void split2_relu(u64 X, uint32_t &whi, uint32_t &wlo)
     wlo = cvt_f16x2_relu_rn(r1, r0);
 }
 // one double-pair (4 hidden units = 2 TMEM columns per piece) of this thread's frame: sigmoid -> split into registers
+template <bool CLAMP = true>
 __device__ __forceinline__ void compute_dpair(uint32_t sP_addr, int dp, u64 yy, uint32_t *vh, uint32_t *vl) {
     u64 g0, g1;
-    recip4(denom2(sP_addr, 2 * dp, yy), denom2(sP_addr, 2 * dp + 1, yy), g0, g1);
+    recip4(denom2<CLAMP>(sP_addr, 2 * dp, yy), denom2<CLAMP>(sP_addr, 2 * dp + 1, yy), g0, g1);
     split2_pre(g0, vh[0], vl[0]);
     split2_pre(g1, vh[1], vl[1]);
 }
@@ -417,6 +424,7 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
     constexpr uint32_t kLBO2 = (2 * N2 / 8) * 128;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint32_t tmem_base_s;
+    __shared__ float y_safe_s;   // |y| up to which no sigmoid exponent exceeds 29.5 (the producers' clamp-free path)
     __shared__ __align__(8) uint64_t d_full[2], slot_free[2], a_full[4], d2_full[2];
     // a_full: one barrier per issue warp (stage n -> a_full[n mod kAF], phase (n / kAF) & 1), so that every waiter sees every
     // phase of its barrier (two warps alternating on one barrier could not tell phase u-1 from u+1)
@@ -463,6 +471,17 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
         const int off = (k / 8) * (2 * N2 / 8) * 128 + (n2 / 8) * 128 + (n2 % 8) * 16 + (k % 8) * 2;
         *reinterpret_cast<uint16_t *>(sB2 + off) = hi;
         *reinterpret_cast<uint16_t *>(sB2 + off + (N2 / 8) * 128) = lo;
+    }
+    if (tid == 32) {
+        float ys = 3.0e38f;
+        for (int k = 0; k < kH1; k++) {
+            const float kNegLog2e = -1.4426950408889634f;
+            const float w = fabsf(p.w.w1[k] * kNegLog2e), b = fmaf(p.w.b1[k], kNegLog2e, -11.f);
+            // |w| Y + b <= 29.5;  NaN weights fail every comparison below and leave the clamped path
+            const float lim = (b <= 29.5f) ? (w > 0.f ? (29.5f - b) / w : 3.0e38f) : -1.f;
+            ys = (lim < ys) ? lim : ((lim >= ys) ? ys : -1.f);
+        }
+        y_safe_s = ys * 0.999f;
     }
     if (tid == 0) {
 #pragma unroll
@@ -534,6 +553,7 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
 
     if (producer) {
         int rot = 0;  // which of the quadrant's producer warps takes the 25th double-pair in this stage
+        const float y_safe = y_safe_s;
         // MVN_TC_LATE_PUBLISH: the tcgen05.st of stage n are published (wait::st, fence, a_full arrival) after the first
         // double-pair of stage n+1 has been computed into spare registers, so their latency overlaps arithmetic
         bool pending = false;
@@ -581,26 +601,33 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
                     const int part = warp >> 2;
                     const bool extra = rot == part;
                     uint32_t vh[NC + 2], vl[NC + 2];
-#pragma unroll
                     // The slot's barrier is probed in the MIDDLE of the stage's arithmetic: at its end the probe would queue
                     // behind this scheduler's MUFU backlog (pipeline trace: 270 cycles for a wait that succeeds at once).
                     const uint32_t slot_bar = smem_addr(DEC ? &d_full[slot] : &slot_free[slot]);
                     bool slot_ready = false;
+                    // (the overflow clamps of the 100 exponents are skipped when every lane's |y| is below the launch's bound)
+                    auto compute_stage = [&](auto clamp_c) {
+                    constexpr bool CL = decltype(clamp_c)::value;
+#pragma unroll
                     for (int i = 0; i < DP; i++) {
 #if MVN_TC_EXPERIMENT == 4   // bound-finding build (wrong results): half of the sigmoids
                         if (i & 1) { vh[2 * i] = vh[2 * i - 2]; vh[2 * i + 1] = vh[2 * i - 1]; vl[2 * i] = vl[2 * i - 2]; vl[2 * i + 1] = vl[2 * i - 1]; continue; }
 #endif
+                        // (fetching the next stage's sample here as well measured the same and cost a spill)
                         if (MVN_TC_EARLY_PROBE && i == DP / 2) slot_ready = tc::mbar_test(slot_bar, (use & 1) ^ 1);
                         if (MVN_TC_LATE_PUBLISH && i == 0) {
                             uint32_t th[2], tl[2];   // vh / vl may still be read by the stores of the previous stage
-                            tc::compute_dpair(sP_addr, DP * part, yy, th, tl);
+                            tc::compute_dpair<CL>(sP_addr, DP * part, yy, th, tl);
                             if (pending) publish();
                             vh[0] = th[0], vh[1] = th[1], vl[0] = tl[0], vl[1] = tl[1];
                             continue;
                         }
-                        tc::compute_dpair(sP_addr, DP * part + i, yy, vh + 2 * i, vl + 2 * i);
+                        tc::compute_dpair<CL>(sP_addr, DP * part + i, yy, vh + 2 * i, vl + 2 * i);
                     }
-                    if (extra) tc::compute_dpair(sP_addr, 24, yy, vh + NC, vl + NC);
+                    if (extra) tc::compute_dpair<CL>(sP_addr, 24, yy, vh + NC, vl + NC);
+                    };
+                    if (MVN_TC_CLAMP_FREE && __all_sync(0xffffffffu, fabsf(yv) <= y_safe)) compute_stage(std::false_type{});
+                    else compute_stage(std::true_type{});
                     TC_TRACE(1, tid == 0);
                     // (128 / 256 states are bound by the consumers: there the producers park instead of polling, which
                     //  would take issue slots from the consumer warp on their scheduler)

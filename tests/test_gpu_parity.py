@@ -305,6 +305,30 @@ def test_vnet_fused_all_trellis_sizes(mvn, fused_impl, L, B, T):
     assert np.array_equal(mvn.ops.unpack_bits(words, T).cpu().numpy(), dec)
 
 
+@pytest.mark.parametrize('L', [4, 7])
+def test_vnet_fused_saturating_inputs(mvn, fused_impl, L):
+    """Large first-layer weights and outliers in y: sigmoid exponents far beyond fp32 range for some (frame, stage,
+    unit) triples.  The tensor-core kernel's producers take their clamp-free path only while |y| is inside the
+    launch's safe bound, so this batch mixes both paths (and warps where only one lane is outside); every prior must
+    stay finite and inside the tolerance, decisions exact on the kernel's own priors (vnet_detector.py:49-61)."""
+    rng = np.random.RandomState(77 + L)
+    S, B, T = 2 ** L, 515, 40
+    w = [rng.randn(100, 1) * 6.0, rng.randn(100) * 8.0, rng.randn(50, 100) * .15, rng.randn(50) * .1,
+         rng.randn(S, 50) * .3, rng.randn(S) * .1]
+    w = [a.astype(np.float32) for a in w]
+    y = (rng.randn(B, T) * 1.5).astype(np.float32)
+    y[::7, ::5] *= 40.0          # single-lane outliers
+    y[64:96] = y[64:96] * 0.01   # one warp tile entirely inside the bound
+    y[3, 3], y[100, 10] = 3.0e4, -3.0e4
+    dec, pri = mvn.ops.vnet_decode(cu(y), [cu(a) for a in w], return_priors=True)
+    dec, pri = dec.cpu().numpy(), pri.cpu().numpy()
+    assert np.isfinite(pri).all()
+    exact = orc.vnet_priors(y, w, dtype=np.float64)
+    assert rel_to_rowmax(pri, exact) < PRIOR_RTOL
+    ref_own, _ = orc.vnet_decode_from_priors(pri)
+    assert np.array_equal(dec, ref_own)
+
+
 def test_vnet_detector_classes(mvn):
     g = load_golden('vnet')
     w, y = _w(g, 'trained_w'), g['y']
