@@ -53,6 +53,9 @@ namespace mvn {
 #ifndef MVN_TC_CLAMP_FREE
 #define MVN_TC_CLAMP_FREE 0   // clamp-free producer path behind a per-stage |y| vote: L=4 17.6 vs 18.0 G sym/s (second copy of the stage body, spills)
 #endif
+#ifndef MVN_TC_RCP_SHARE
+#define MVN_TC_RCP_SHARE 4
+#endif
 #ifndef MVN_TC_EXPERIMENT
 #define MVN_TC_EXPERIMENT 0   // 1, 2: bound-finding builds of the producers, never shipped
 #endif
@@ -275,6 +278,12 @@ __device__ __forceinline__ u64 denom2(uint32_t sP_addr, int pair, u64 yy) {
 __device__ __forceinline__ void recip4(u64 p, u64 q, u64 &rp, u64 &rq) {
     float m0, m1;
     unpack2(mul2(p, q), m0, m1);                   // (p.x q.x, p.y q.y)
+#if MVN_TC_RCP_SHARE == 2   // two reciprocals per four values: 5 instructions instead of 7, 2 MUFU instead of 1
+    const u64 inv2 = pack2(rcp_approx(m0), rcp_approx(m1));
+    rp = mul2(inv2, q);
+    rq = mul2(inv2, p);
+    return;
+#endif
 #if MVN_TC_EXPERIMENT == 1   // bound-finding build (wrong results): no MUFU.RCP
     const float r = m0 * m1 + 3.f;
 #else
