@@ -56,6 +56,9 @@ namespace mvn {
 #ifndef MVN_TC_RCP_SHARE
 #define MVN_TC_RCP_SHARE 4
 #endif
+#ifndef MVN_TC_CONV_PREFETCH
+#define MVN_TC_CONV_PREFETCH 0   // converter keeps the next chunk's tcgen05.ld in flight: 973 -> 914 cycles per stage, throughput unchanged (17.7 vs 18.0)
+#endif
 #ifndef MVN_TC_EXPERIMENT
 #define MVN_TC_EXPERIMENT 0   // 1, 2: bound-finding builds of the producers, never shipped
 #endif
@@ -178,6 +181,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t addr, float *r) {
         : "r"(addr));
 #pragma unroll
     for (int i = 0; i < 16; i++) r[i] = __uint_as_float(u[i]);
+}
+// tcgen05.wait::ld that also "produces" the 16 registers of an earlier tcgen05.ld: with a load kept in flight across
+// other work (h2_to_tmem prefetches the next chunk) the compiler must not move a use of those registers above the wait
+__device__ __forceinline__ void tmem_wait_ld16(float *r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]), "+f"(r[4]), "+f"(r[5]), "+f"(r[6]), "+f"(r[7]), "+f"(r[8]),
+                   "+f"(r[9]), "+f"(r[10]), "+f"(r[11]), "+f"(r[12]), "+f"(r[13]), "+f"(r[14]), "+f"(r[15]));
 }
 // try_wait with a suspend-time hint: the waiting warp is parked by the hardware until the phase completes (or the
 // hint expires) instead of spinning.  A spinning warp competes for the issue slots of its scheduler; the MMA warp
@@ -359,6 +369,32 @@ template <int MODE>
 __device__ __forceinline__ void h2_to_tmem(uint32_t slot_lane) {
     using LY = Lay<MODE>;
     constexpr bool DEC = (MODE == 1);
+    if constexpr (DEC && MVN_TC_CONV_PREFETCH) {
+        // one accumulator: the tcgen05.ld of chunk c0 + 1 is in flight while chunk c0 is converted (TMEM loads queue behind
+        // the MUFU backlog of the producers that share the scheduler)
+        float m[2][16];
+        tmem_ld16(slot_lane + oDm, m[0]);
+#pragma unroll
+        for (int c0 = 0; c0 < kK2Steps; c0++) {
+            tmem_wait_ld16(m[c0 & 1]);
+            if (c0 + 1 < kK2Steps) tmem_ld16(slot_lane + oDm + 16 * (c0 + 1), m[(c0 + 1) & 1]);
+            uint32_t vh[8], vl[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int k = 16 * c0 + 2 * q;
+                if (k + 1 < kH2) {
+                    split2_relu(pack2(m[c0 & 1][2 * q], m[c0 & 1][2 * q + 1]), vh[q], vl[q]);
+                } else {  // k2 = 50: bias column (1.0 in the low half); beyond: zero padding
+                    vh[q] = (k == kH2) ? 0x00003c00u : 0u;
+                    vl[q] = 0u;
+                }
+            }
+            tmem_st8(slot_lane + LY::hh(c0), vh);
+            tmem_st8(slot_lane + LY::hl(c0), vl);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;");
+        return;
+    }
 #pragma unroll
     for (int c0 = 0; c0 < kK2Steps; c0++) {   // 16 hidden units = 8 columns per step
         float m[16], c[16];
