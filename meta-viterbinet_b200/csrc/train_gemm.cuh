@@ -13,6 +13,7 @@
 //   G1  H2T = relu(W2 H1T + b2)          G2  ZT = W3 H2T + b3      (GEMMs, K = 100 / 52)
 //   E2  softmax-CE per symbol: loss, dZ over ZT, db3
 //   G3  dW3 += dZT H2T^T   (K = symbols)  ||  G4  DA2T = [H2>0] W3^T dZT  (+ db2)          one phase, one block list
+//       (the second half of G3's K range runs in the next phase: MVN_TRAIN_SPLIT_DW3)
 //   G5  dW2 += DA2T H1T^T  (K = symbols)  ||  G6  dA1 = (W2^T DA2T) h(1-h) -> dW1, db1      one phase, never stored
 // and the forward-over-reverse (tangent) pass runs the same schedule with a second accumulator set
 //   R{A B} = Av B + A Rb,  which is what MAML's  g_q - meta_lr H_s(theta) g_q  needs.
@@ -30,6 +31,9 @@ namespace tg {
 
 #ifndef MVN_TRAIN_THREADS
 #define MVN_TRAIN_THREADS 512   // 16 warps: measured 795k MAML steps/s vs 700k at 256 threads and 770k at 384 (profiles/r02_train_bench.txt)
+#endif
+#ifndef MVN_TRAIN_SPLIT_DW3
+#define MVN_TRAIN_SPLIT_DW3 1
 #endif
 constexpr int kThreads = MVN_TRAIN_THREADS, kWarps = kThreads / 32;
 constexpr int kH2P = 52;   // hidden-2 width padded to a multiple of 4
@@ -367,8 +371,14 @@ __device__ __forceinline__ float pass(const Smem<S> &sm, const float *__restrict
                     });
                 __syncthreads();
             }
-            for (int blk = warp; blk < (MERGE ? nb3 : 0) + nb4; blk += kWarps) {
-                if (blk < nb4) {
+            // MERGE: dW3 has only nb3 = 2 blocks with the whole symbol range as K, against nb4 = 20 short blocks of dA2: the
+            // first half of its K range runs here (those two units first: longest first), the second half in the next phase
+            // next to dW2 / dA1 (H2T and dZT stay intact there), where it accumulates into the same G tiles after the barrier.
+            const int ng_a = MERGE ? (MVN_TRAIN_SPLIT_DW3 ? (ng + 1) / 2 : ng) : 0;
+            const GemmArgs g3a{g3.A, g3.Av, ldn, g3.B, g3.Rb, ldn, S, kH2, ng_a};
+            for (int u = warp; u < (MERGE ? nb3 : 0) + nb4; u += kWarps) {
+                const int blk = u - (MERGE ? nb3 : 0);
+                if (blk >= 0) {
                     gemm_block<AM, BN, GM, false>(g4, blk, [&](const Tile &t, float (&acc)[4][4], float (&racc)[4][4]) {
 #pragma unroll
                         for (int i = 0; i < 4; i++) {
@@ -391,7 +401,7 @@ __device__ __forceinline__ float pass(const Smem<S> &sm, const float *__restrict
                         }
                     });
                 } else {
-                    gemm_block<AK, BK, WM, true>(g3, blk - nb4, [&](const Tile &t, float (&acc)[4][4], float (&racc)[4][4]) {
+                    gemm_block<AK, BK, WM, true>(g3a, u, [&](const Tile &t, float (&acc)[4][4], float (&racc)[4][4]) {
                         accumulate_tile(G + LY::w3, kH2P, t, TAN ? racc : acc, scale);
                     });
                 }
@@ -405,8 +415,16 @@ __device__ __forceinline__ float pass(const Smem<S> &sm, const float *__restrict
             const GemmArgs g5{sm.DA2T, sm.RDA2T, ldn, sm.H1T, sm.RH1T, ldn, kH2, kH1, ng};
             const GemmArgs g6{W + LY::w2, V + LY::w2, kH1, sm.DA2T, sm.RDA2T, ldn, kH1, n4, kH2P / 4};
             const int nb5 = num_blocks(g5), nb6 = num_blocks(g6);
-            for (int blk = warp; blk < nb5 + nb6; blk += kWarps) {
-                if (blk < nb6) {
+            // second half of dW3's K range (MERGE only, see above)
+            const int ng_a = (MERGE && MVN_TRAIN_SPLIT_DW3) ? (ng + 1) / 2 : ng;
+            const GemmArgs g3b{sm.ZT + 4 * ng_a, sm.RZT + 4 * ng_a, ldn, sm.H2T + 4 * ng_a, sm.RH2T + 4 * ng_a, ldn, S, kH2, ng - ng_a};
+            const int nb3b = (ng > ng_a) ? num_blocks(g3b) : 0;
+            for (int blk = warp; blk < nb5 + nb6 + nb3b; blk += kWarps) {
+                if (blk >= nb5 + nb6) {
+                    gemm_block<AK, BK, WM, true>(g3b, blk - nb5 - nb6, [&](const Tile &t, float (&acc)[4][4], float (&racc)[4][4]) {
+                        accumulate_tile(G + LY::w3, kH2P, t, TAN ? racc : acc, scale);
+                    });
+                } else if (blk < nb6) {
                     gemm_block<AM, BN, GM, false>(g6, blk, [&](const Tile &t, float (&acc)[4][4], float (&racc)[4][4]) {
                         const bool cok = t.c[0] >= 0;
                         const float4 yv = cok ? lds4(sm.y + t.c[0]) : make_float4(0.f, 0.f, 0.f, 0.f);
