@@ -72,24 +72,40 @@ constexpr int kACols = kK / 2;                // 32-bit TMEM columns per A piece
 constexpr int kSlotCols = 256;                // slot stride; 240 used: D_main | D_corr | A_hi | A_lo
 constexpr int oDm = 0, oDc = kN, oAh = 2 * kN, oAl = 2 * kN + kACols;   // round-1 layout (L >= 7): D_main | D_corr | A_hi | A_lo
 // TMEM layouts of one slot (240 of its 256 columns):
-//   mode 0 (L >= 7)      D_main (64) | D_corr (64) | A_hi (56) | A_lo (56); h2 reuses the first 32 columns of A_hi / A_lo,
+//   mode 0 (L == 7)      D_main (64) | D_corr (64) | A_hi (56) | A_lo (56); h2 reuses the first 32 columns of A_hi / A_lo,
 //                        so the producers may refill A only after the consumers have released the slot
 //   mode 1 ("merged")    D (64) | A_hi (56) | A_lo (56) | H2_hi (32) | H2_lo (32): ONE layer-2 accumulator (the correction
 //                        chain is folded in on the tensor core with scale-input-d, 21 MMAs of N = 64)
 //   mode 2 ("in place")  D_main | D_corr | A_hi | A_lo as mode 0 (7 MMAs of N = 128 + 7 of N = 64), but the converter writes
 //                        the h2 pieces of k-step j over the 16 D_corr columns it has just read (hi: 8 columns, lo: 8)
-// In modes 1 and 2 the A columns are free again as soon as the layer-2 MMAs have read them: the producers wait for d_full
-// of the slot's previous use, not for its consumers.
+//   mode 3 (L == 8)      A_hi (56) | A_lo (56) ONCE, then per slot D_main (64) | D_corr (64) | H2_hi (32) | H2_lo (32) = 496 columns:
+//                        128 / 256 states need all 128 accumulator columns for the priors, so h2 gets columns of its own by
+//                        giving up the second A buffer — the producers hold the next stage in registers anyway and only
+//                        need the layer-2 MMAs of the PREVIOUS stage to have read A
+// In modes 1, 2 and 3 the A columns are free again as soon as the layer-2 MMAs have read them: the producers wait for a
+// d_full, not for the consumers (mode 0: for the consumers of the slot's previous use).
 #ifndef MVN_TC_LAYOUT
 #define MVN_TC_LAYOUT 1
 #endif
+#ifndef MVN_TC_LAYOUT_L7
+#define MVN_TC_LAYOUT_L7 0   // 128 states: 0 (round-1 layout) or 3
+#endif
+#ifndef MVN_TC_LAYOUT_L8
+#define MVN_TC_LAYOUT_L8 3   // 256 states: 0 or 3
+#endif
 template <int MODE>
 struct Lay {
-    static constexpr int D = 0;
-    static constexpr int Ah = MODE == 1 ? kN : 2 * kN, Al = Ah + kACols;
-    // layer-3 A operand: TMEM column of the hi / lo piece of k-step j (16 hidden units = 8 columns)
-    __host__ __device__ static constexpr int hh(int j) { return MODE == 0 ? Ah + 8 * j : MODE == 1 ? Al + kACols + 8 * j : kN + 16 * j; }
-    __host__ __device__ static constexpr int hl(int j) { return MODE == 0 ? Al + 8 * j : MODE == 1 ? Al + kACols + 32 + 8 * j : kN + 16 * j + 8; }
+    // TMEM column of the slot's accumulators (D) and of the layer-2 A operand (A_hi; A_lo follows kACols later).
+    // Mode 3 has ONE A buffer for both slots.
+    __host__ __device__ static constexpr int d_col(int slot) { return MODE == 3 ? 2 * kACols + slot * (2 * kN + 64) : slot * kSlotCols; }
+    __host__ __device__ static constexpr int a_col(int slot) { return MODE == 3 ? 0 : slot * kSlotCols + (MODE == 1 ? kN : 2 * kN); }
+    // layer-3 A operand (h2): column of the hi / lo piece of k-step j (16 hidden units = 8 columns), relative to d_col
+    __host__ __device__ static constexpr int hh(int j) {
+        return MODE == 0 ? 2 * kN + 8 * j : MODE == 1 ? kN + 2 * kACols + 8 * j : MODE == 2 ? kN + 16 * j : 2 * kN + 8 * j;
+    }
+    __host__ __device__ static constexpr int hl(int j) {
+        return MODE == 0 ? 2 * kN + kACols + 8 * j : MODE == 1 ? kN + 2 * kACols + 32 + 8 * j : MODE == 2 ? kN + 16 * j + 8 : 2 * kN + 32 + 8 * j;
+    }
 };
 constexpr float kScale = 2048.f, kInvScale = 1.f / 2048.f;
 // B operand of layer 2: the hi and lo pieces of W2 stacked along N (rows 0..63 hi, 64..127 lo), so ONE N=128 MMA per
@@ -454,7 +470,9 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
     //         metrics of the 128 frames (128 KB) fill the shared memory, so this instance stages no tiles at all: the
     //         producers read their sample straight from global memory (one L1-resident line per frame and 32 stages),
     //         the consumers their targets.
-    constexpr int LAYM = (L <= 6) ? MVN_TC_LAYOUT : 0;   // TMEM layout of a slot (tc::Lay)
+    // TMEM layout of a slot (tc::Lay).  Measured: mode 3 at 128 states 10.9 vs 11.8 G sym/s (mode 0), at 256 states 5.64 vs 5.45
+    constexpr int LAYM = (L <= 6) ? MVN_TC_LAYOUT : (L == 7) ? MVN_TC_LAYOUT_L7 : MVN_TC_LAYOUT_L8;
+    constexpr bool SINGLE_A = (LAYM == 3);       // one A buffer: the producers wait for the layer-2 MMAs of the previous STAGE
     constexpr bool DEC = (LAYM != 0);            // h2 outside the A columns: producers wait for the layer-2 MMAs, not the consumers
     constexpr bool L2MERGED = (LAYM == 1);       // one layer-2 accumulator (scale-input-d)
     using LY = tc::Lay<LAYM>;
@@ -557,11 +575,11 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
         const uint32_t z[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
         for (int sl = 0; sl < 2; sl++) {
-            const uint32_t base = tmem + sl * tc::kSlotCols + lane_base;
-            tc::tmem_st2(base + LY::Ah + 50, 0x00006800u, 0u);
-            tc::tmem_st4(base + LY::Ah + 52, z);
-            tc::tmem_st2(base + LY::Al + 50, 0u, 0u);
-            tc::tmem_st4(base + LY::Al + 52, z);
+            const uint32_t base = tmem + LY::a_col(sl) + lane_base;
+            tc::tmem_st2(base + 50, 0x00006800u, 0u);
+            tc::tmem_st4(base + 52, z);
+            tc::tmem_st2(base + tc::kACols + 50, 0u, 0u);
+            tc::tmem_st4(base + tc::kACols + 52, z);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;");
     }
@@ -631,7 +649,7 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
 #pragma unroll 1
                 for (int tt = 0; tt < t_end; tt++, n++) {
                     const uint32_t slot = n & 1, use = n >> 1;
-                    const uint32_t slot_lane = tmem + slot * tc::kSlotCols + lane_base;
+                    const uint32_t a_lane = tmem + LY::a_col(slot) + lane_base;
                     const float yv = DIRECT ? __ldg(yrow + tt) : tile[lane * kTileLd + tt];
                     const u64 yy = pack2(yv, yv);
                     // Compute this stage's pieces into registers BEFORE waiting for the slot: the sigmoid/split work
@@ -648,7 +666,10 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
                     uint32_t vh[NC + 2], vl[NC + 2];
                     // The slot's barrier is probed in the MIDDLE of the stage's arithmetic: at its end the probe would queue
                     // behind this scheduler's MUFU backlog (pipeline trace: 270 cycles for a wait that succeeds at once).
-                    const uint32_t slot_bar = smem_addr(DEC ? &d_full[slot] : &slot_free[slot]);
+                    // (SINGLE_A: the previous stage's layer-2 MMAs, i.e. the OTHER slot's d_full; a fresh barrier passes a wait
+                    //  for the phase before its first, which covers n = 0)
+                    const uint32_t slot_bar = smem_addr(SINGLE_A ? &d_full[(n - 1) & 1] : DEC ? &d_full[slot] : &slot_free[slot]);
+                    const uint32_t slot_par = SINGLE_A ? (((n - 1) >> 1) & 1) : ((use & 1) ^ 1);
                     bool slot_ready = false;
                     // (the overflow clamps of the 100 exponents are skipped when every lane's |y| is below the launch's bound)
                     auto compute_stage = [&](auto clamp_c) {
@@ -659,7 +680,7 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
                         if (i & 1) { vh[2 * i] = vh[2 * i - 2]; vh[2 * i + 1] = vh[2 * i - 1]; vl[2 * i] = vl[2 * i - 2]; vl[2 * i + 1] = vl[2 * i - 1]; continue; }
 #endif
                         // (fetching the next stage's sample here as well measured the same and cost a spill)
-                        if (MVN_TC_EARLY_PROBE && i == DP / 2) slot_ready = tc::mbar_test(slot_bar, (use & 1) ^ 1);
+                        if (MVN_TC_EARLY_PROBE && i == DP / 2) slot_ready = tc::mbar_test(slot_bar, slot_par);
                         if (MVN_TC_LATE_PUBLISH && i == 0) {
                             uint32_t th[2], tl[2];   // vh / vl may still be read by the stores of the previous stage
                             tc::compute_dpair<CL>(sP_addr, DP * part, yy, th, tl);
@@ -678,12 +699,12 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
                     //  would take issue slots from the consumer warp on their scheduler)
                     // DEC: the A columns are free once the layer-2 MMAs of the slot's previous use have read them (d_full);
                     // round-1 layout: once the consumers have released the slot (h2 lives in the A columns)
-                    if (!slot_ready) tc::mbar_wait<(MVN_PROD_PARK || L >= 7)>(slot_bar, (use & 1) ^ 1, timeout_flag);
+                    if (!slot_ready) tc::mbar_wait<(MVN_PROD_PARK || L >= 7)>(slot_bar, slot_par, timeout_flag);
                     TC_TRACE(28, tid == 0);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     TC_TRACE(2, tid == 0);
                     {
-                        const uint32_t ah = slot_lane + LY::Ah + NC * part, al = slot_lane + LY::Al + NC * part;
+                        const uint32_t ah = a_lane + NC * part, al = a_lane + tc::kACols + NC * part;
                         if constexpr (NC == 16) {
                             tc::tmem_st16p(ah, vh);
                             tc::tmem_st16p(al, vl);
@@ -694,8 +715,8 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
                             tc::tmem_st4(al + 8, vl + 8);
                         }
                         if (extra) {
-                            tc::tmem_st2(slot_lane + LY::Ah + 48, vh[NC], vh[NC + 1]);
-                            tc::tmem_st2(slot_lane + LY::Al + 48, vl[NC], vl[NC + 1]);
+                            tc::tmem_st2(a_lane + 48, vh[NC], vh[NC + 1]);
+                            tc::tmem_st2(a_lane + tc::kACols + 48, vl[NC], vl[NC + 1]);
                         }
                     }
                     rot = rot == tc::kProdParts - 1 ? 0 : rot + 1;
@@ -739,29 +760,29 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
                     }
                     TC_TRACE(15, lane == 0);
                     if (tc::elect_one()) {
-                        const uint32_t ts = tmem + slot * tc::kSlotCols;
+                        const uint32_t ts = tmem + LY::d_col(slot), ah = tmem + LY::a_col(slot), al = ah + tc::kACols;
                         if constexpr (!L2MERGED) {
 #pragma unroll
                             for (int j = 0; j < tc::kKSteps; j++)   // D_main | D_corr = A_hi [B_hi | B_lo]
-                                tc::mma_f16_ts(ts + tc::oDm, ts + LY::Ah + j * 8, tc::b_desc(sB_addr + uint32_t(2 * j) * tc::kLBO), idescw,
+                                tc::mma_f16_ts(ts + tc::oDm, ah + j * 8, tc::b_desc(sB_addr + uint32_t(2 * j) * tc::kLBO), idescw,
                                                j > 0);
 #pragma unroll
                             for (int j = 0; j < tc::kKSteps; j++)   // D_main += A_lo B_hi (the remainder of the pre-scaled A is unscaled)
-                                tc::mma_f16_ts(ts + tc::oDm, ts + LY::Al + j * 8, tc::b_desc(sB_addr + uint32_t(2 * j) * tc::kLBO), idesc, 1);
+                                tc::mma_f16_ts(ts + tc::oDm, al + j * 8, tc::b_desc(sB_addr + uint32_t(2 * j) * tc::kLBO), idesc, 1);
                         } else {
                             constexpr uint32_t kLoRowsB = (tc::kN / 8) * 128;   // W2_lo rows inside a k-chunk of the stacked B
 #pragma unroll
                             for (int j = 0; j < tc::kKSteps; j++)   // D = A_hi B_lo (the 2048-scaled correction)
-                                tc::mma_f16_ts(ts + tc::oDm, ts + LY::Ah + j * 8, tc::b_desc(sB_addr + uint32_t(2 * j) * tc::kLBO + kLoRowsB), idesc,
+                                tc::mma_f16_ts(ts + tc::oDm, ah + j * 8, tc::b_desc(sB_addr + uint32_t(2 * j) * tc::kLBO + kLoRowsB), idesc,
                                                j > 0);
                             // D = A_hi B_hi + D / 2048: scale-input-d on the first MMA of the main chain
-                            tc::mma_f16_ts_scale11(ts + tc::oDm, ts + LY::Ah, tc::b_desc(sB_addr), idesc);
+                            tc::mma_f16_ts_scale11(ts + tc::oDm, ah, tc::b_desc(sB_addr), idesc);
 #pragma unroll
                             for (int j = 1; j < tc::kKSteps; j++)
-                                tc::mma_f16_ts(ts + tc::oDm, ts + LY::Ah + j * 8, tc::b_desc(sB_addr + uint32_t(2 * j) * tc::kLBO), idesc, 1);
+                                tc::mma_f16_ts(ts + tc::oDm, ah + j * 8, tc::b_desc(sB_addr + uint32_t(2 * j) * tc::kLBO), idesc, 1);
 #pragma unroll
                             for (int j = 0; j < tc::kKSteps; j++)   // D += A_lo B_hi (the remainder of the pre-scaled A is unscaled)
-                                tc::mma_f16_ts(ts + tc::oDm, ts + LY::Al + j * 8, tc::b_desc(sB_addr + uint32_t(2 * j) * tc::kLBO), idesc, 1);
+                                tc::mma_f16_ts(ts + tc::oDm, al + j * 8, tc::b_desc(sB_addr + uint32_t(2 * j) * tc::kLBO), idesc, 1);
                         }
                         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                             smem_addr(&d_full[slot])));
@@ -780,7 +801,7 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
 #pragma unroll 1
                 for (int tt = 0; tt < t_end; tt++, n++) {
                     const uint32_t slot = n & 1, use = n >> 1;
-                    const uint32_t ts = tmem + slot * tc::kSlotCols, slot_lane = ts + lane_base;
+                    const uint32_t ts = tmem + LY::d_col(slot), slot_lane = ts + lane_base;
                     TC_TRACE(6, warp == tc::kProdWarps && lane == 0);
                     tc::mbar_wait<MVN_CONS_PARK>(smem_addr(&d_full[slot]), use & 1, timeout_flag);
                     asm volatile("tcgen05.fence::after_thread_sync;");
@@ -855,7 +876,7 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
 #pragma unroll 1
                 for (int tt = 0; tt < t_end; tt++, n++) {
                     const uint32_t slot = n & 1, use = n >> 1;
-                    const uint32_t ts = tmem + slot * tc::kSlotCols, slot_lane = ts + lane_base;
+                    const uint32_t ts = tmem + LY::d_col(slot), slot_lane = ts + lane_base;
                     if constexpr (!MLSE) {
                         if (active) bits |= tr.decide() << tt;   // metrics entering this stage; overlaps the wait
                     }

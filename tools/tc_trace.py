@@ -1,5 +1,5 @@
 """Pipeline timeline of the tcgen05 fused kernel (debug library built with -DMVN_TC_TRACE).
-Usage: python tools/tc_trace.py"""
+Usage: python tools/tc_trace.py [memory_length]"""
 import ctypes
 import os
 import sys
@@ -15,7 +15,11 @@ _lib.LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libmvn
 import meta_viterbinet_b200 as mvn
 
 dev = torch.device('cuda', 0)
-w = bench.make_weights(torch, dev)
+L = int(sys.argv[1]) if len(sys.argv) > 1 else 4   # memory length (2^L states)
+torch.manual_seed(0)
+_net = torch.nn.Sequential(torch.nn.Linear(1, 100), torch.nn.Sigmoid(), torch.nn.Linear(100, 50), torch.nn.ReLU(),
+                           torch.nn.Linear(50, 2 ** L))
+w = [q.detach().to(dev).contiguous() for q in _net.parameters()]
 bits, y = bench.synth_frames(torch, dev, 148 * 128 * 4, 10, 1)
 for _ in range(2):
     mvn.ops.vnet_decode(y, w)
