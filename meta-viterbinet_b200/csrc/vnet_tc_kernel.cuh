@@ -59,6 +59,9 @@ namespace mvn {
 #ifndef MVN_TC_CONV_PREFETCH
 #define MVN_TC_CONV_PREFETCH 0   // converter keeps the next chunk's tcgen05.ld in flight: 973 -> 914 cycles per stage, throughput unchanged (17.7 vs 18.0)
 #endif
+#ifndef MVN_TC_PARK_MINL
+#define MVN_TC_PARK_MINL 7   // producers park (instead of polling) from this memory length on
+#endif
 #ifndef MVN_TC_EXPERIMENT
 #define MVN_TC_EXPERIMENT 0   // 1, 2: bound-finding builds of the producers, never shipped
 #endif
@@ -699,7 +702,7 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
                     //  would take issue slots from the consumer warp on their scheduler)
                     // DEC: the A columns are free once the layer-2 MMAs of the slot's previous use have read them (d_full);
                     // round-1 layout: once the consumers have released the slot (h2 lives in the A columns)
-                    if (!slot_ready) tc::mbar_wait<(MVN_PROD_PARK || L >= 7)>(slot_bar, slot_par, timeout_flag);
+                    if (!slot_ready) tc::mbar_wait<(MVN_PROD_PARK || L >= MVN_TC_PARK_MINL)>(slot_bar, slot_par, timeout_flag);
                     TC_TRACE(28, tid == 0);
                     asm volatile("tcgen05.fence::after_thread_sync;");
                     TC_TRACE(2, tid == 0);
