@@ -363,7 +363,7 @@ static int launch_tc_mode(VnetParams p, cudaStream_t st) {
 #ifdef MVN_TC_TRACE
     MVN_CUDA(cudaGetSymbolAddress(&trace, g_tc_trace));
 #endif
-    kern<<<grid, tc::kThreadsTc, smem, st>>>(p, flag, static_cast<long long *>(trace));
+    kern<<<grid, tc::Roles<L>::kThreads, smem, st>>>(p, flag, static_cast<long long *>(trace));
     note_launch();
     MVN_CUDA(cudaGetLastError());
     return MVN_OK;

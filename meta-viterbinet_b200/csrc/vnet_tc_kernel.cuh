@@ -133,6 +133,29 @@ static_assert(kProdWarps == 12 || kProdWarps == 16, "24 double-pairs of hidden u
 #endif
 constexpr int kMmaWarps = MVN_TC_MMA_WARPS;
 constexpr int kThreadsTc = 32 * (kProdWarps + kConvWarps + kConsWarps + kMmaWarps);
+// Warp roles per memory length.  At 128 / 256 states one consumer warp per 32 frames is busy 70-90 % of a stage (pipeline
+// traces), so MVN_TC_DUAL_CONS=1 gives every TMEM lane quadrant TWO consumer warps that split the source-state chunks of a
+// stage (= its destination states; the metrics are in shared memory, only the even / odd minima of the decision are
+// exchanged, one named barrier per pair and stage).  Bit-exact, but NOT faster — 12 producers + 8 consumers (28 warps, 72
+// registers): 11.4 / 5.64 G sym/s at 128 / 256 states against 11.8 / 5.64 with one consumer warp; 8 + 8 (24 warps): 11.1 /
+// 5.04.  The two warps of a pair sit on the same scheduler (a warp reads the TMEM lanes of quadrant warp % 4) and the time
+// of a chunk is the latency of its tcgen05.ld / LDS / STS through that scheduler's MIO queue, which they share.  Off.
+#ifndef MVN_TC_DUAL_CONS
+#define MVN_TC_DUAL_CONS 0
+#endif
+#ifndef MVN_TC_DUAL_PROD
+#define MVN_TC_DUAL_PROD 12
+#endif
+template <int L>
+struct Roles {
+    static constexpr bool DUAL = MVN_TC_DUAL_CONS && L >= 7 && kProdWarps == 12;
+    // MVN_TC_DUAL_PROD: producer warps of the DUAL instances.  8 keeps the block at 24 warps of 80 registers, but a warp's 12
+    // double-pairs then go through the registers in two halves and the second half is computed after the slot has been
+    // acquired — on the critical loop at 128 states (measured: slower than one consumer warp).  12 = 28 warps of 72 registers.
+    static constexpr int PW = DUAL ? MVN_TC_DUAL_PROD : kProdWarps, KW = DUAL ? 8 : kConsWarps, PARTS = PW / 4;
+    static constexpr int kWarps = PW + kConvWarps + KW + kMmaWarps, kThreads = 32 * kWarps;
+    static constexpr int kMaxReg = (kWarps > 24) ? 72 : 80;   // 7 warps per scheduler need <= 73 registers
+};
 // layer 3 on the tensor core as well: D2[128 x 16] = h2[128 x 64] W3^T, K2 = 50 hidden units + bias column, padded
 // (N2 = max(16, n_states) output columns, so up to 64 states fit the slot's 64-column D regions)
 constexpr int kK2 = 64, kK2Steps = kK2 / 16;
@@ -461,7 +484,7 @@ __device__ __forceinline__ void h2_to_tmem(uint32_t slot_lane) {
 #endif
 
 template <int L, bool MLSE>
-__global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch timeout_flag, long long *trace) {
+__global__ void __maxnreg__(tc::Roles<L>::kMaxReg) vnet_decode_tc_kernel(VnetParams p, tc::TcWatch timeout_flag, long long *trace) {
     static_assert(L <= 8, "tcgen05 variant: memory_length 1..8");
     // L <= 5: priors_main | priors_corr side by side inside the slot's 64 accumulator columns (one N = 2 N2 MMA per k-step).
     // L == 6: 64 priors: the correction chain is folded into the main chain (scale-input-d), as for L == 7.
@@ -484,32 +507,36 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
     constexpr int kQ = 4;                        // active TMEM lane quadrants = 32-frame warp tiles per CTA tile
     constexpr bool DIRECT = (L == 8);            // no staged tiles (see above)
     using D = TrellisDims<L>;
-    constexpr int S = D::S, C = D::C, NCH = D::NCH, NW = tc::kProdWarps + tc::kConvWarps + tc::kConsWarps;
+    using RL = tc::Roles<L>;
+    constexpr int PW = RL::PW, KW = RL::KW, PARTS = RL::PARTS;   // producer / consumer warps, producer warps per quadrant
+    constexpr bool DUAL = RL::DUAL;
+    constexpr int S = D::S, C = D::C, NCH = D::NCH, NW = PW + tc::kConvWarps + KW;
     constexpr int N2 = tc::n2_of(S), kB2Bytes = tc::b2_bytes(S);
     constexpr int N3 = N2 / NPASS;               // output columns of one layer-3 pass
     constexpr uint32_t kLBO2 = (2 * N2 / 8) * 128;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint32_t tmem_base_s;
+    __shared__ float cons_xchg[tc::Roles<L>::DUAL ? 2 * 2 * 32 * 4 : 1];   // DUAL: [stage parity][even | odd][frame] minima of the second consumer warp
     __shared__ float y_safe_s;   // |y| up to which no sigmoid exponent exceeds 29.5 (the producers' clamp-free path)
     __shared__ __align__(8) uint64_t d_full[2], slot_free[2], a_full[4], d2_full[2];
     // a_full: one barrier per issue warp (stage n -> a_full[n mod kAF], phase (n / kAF) & 1), so that every waiter sees every
     // phase of its barrier (two warps alternating on one barrier could not tell phase u-1 from u+1)
     constexpr uint32_t kAF = tc::kMmaWarps > 2 ? 4 : 2;
-    constexpr int NT_TILES = DIRECT ? 0 : (tc::kProdParts + 1) * kQ;             // producers and consumers stage tiles
+    constexpr int NT_TILES = DIRECT ? 0 : (PARTS + 1) * kQ;             // producers and consumers stage tiles
     uint8_t *sB = smem_raw;                                                      // W2 pieces, hi rows | lo rows
     float *tiles = reinterpret_cast<float *>(smem_raw + tc::kBBytes);            // one 32x32 tile per such warp
     float *sP = tiles + NT_TILES * kTileFloats;                                  // [56][4] pair table for the packed sigmoid
     uint8_t *sB2 = reinterpret_cast<uint8_t *>(sP + 4 * (tc::kK / 2));           // W3 (+ b3 column) pieces: hi | lo
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, quad = warp & 3;
-    const bool producer = warp < tc::kProdWarps;
-    const bool converter = !producer && warp < tc::kProdWarps + tc::kConvWarps;
+    const bool producer = warp < PW;
+    const bool converter = !producer && warp < PW + tc::kConvWarps;
     const bool mma_warp = warp >= NW;
     // tiles: one per producer warp (y) and one per consumer warp (targets); converters and the MMA warp use none
     const bool active = quad < kQ;
-    float *tile = tiles + (DIRECT ? 0 : (producer ? (warp >> 2) * kQ + (active ? quad : 0) : tc::kProdParts * kQ + (active ? quad : 0)) * kTileFloats);
+    float *tile = tiles + (DIRECT ? 0 : (producer ? (warp >> 2) * kQ + (active ? quad : 0) : PARTS * kQ + (active ? quad : 0)) * kTileFloats);
 
     // ---- W2 (and b2 as column k=100) -> fp16 hi / scaled-lo pieces in the canonical K-major layout
-    for (int idx = tid; idx < tc::kN * tc::kK; idx += tc::kThreadsTc) {
+    for (int idx = tid; idx < tc::kN * tc::kK; idx += RL::kThreads) {
         const int n = idx / tc::kK, k = idx % tc::kK;
         float w = 0.f;
         if (n < kH2) w = k < kH1 ? p.w.w2[n * kH1 + k] : (k == kH1 ? p.w.b2[n] : 0.f);
@@ -519,7 +546,7 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
         *reinterpret_cast<uint16_t *>(sB + off) = hi;
         *reinterpret_cast<uint16_t *>(sB + off + (tc::kN / 8) * 128) = lo;
     }
-    for (int i = tid; i < tc::kK / 2; i += tc::kThreadsTc) {
+    for (int i = tid; i < tc::kK / 2; i += RL::kThreads) {
         const float kNegLog2e = -1.4426950408889634f;
         const int k = 2 * i;
         sP[4 * i + 0] = k < kH1 ? p.w.w1[k] * kNegLog2e : 0.f;
@@ -528,7 +555,7 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
         sP[4 * i + 3] = k + 1 < kH1 ? fmaf(p.w.b1[k + 1], kNegLog2e, -11.f) : 0.f;
     }
     // ---- W3 (and b3 as column k2=50) -> fp16 pieces, canonical K-major layout with N2 rows (states)
-    for (int idx = tid; idx < N2 * tc::kK2; idx += tc::kThreadsTc) {
+    for (int idx = tid; idx < N2 * tc::kK2; idx += RL::kThreads) {
         const int n2 = idx / tc::kK2, k = idx % tc::kK2;
         float w = 0.f;
         if (n2 < S) w = k < kH2 ? p.w.w3[n2 * kH2 + k] : (k == kH2 ? p.w.b3[n2] : 0.f);
@@ -554,11 +581,11 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
         for (int s = 0; s < 2; s++) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&d_full[s])));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&d2_full[s])));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&slot_free[s])), "n"(tc::kConsWarps));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&slot_free[s])), "n"(KW));
         }
 #pragma unroll
         for (int s = 0; s < 4; s++)
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&a_full[s])), "n"(tc::kProdWarps));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&a_full[s])), "n"(PW));
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     if (warp == 0) {
@@ -663,7 +690,8 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
                     // = columns [2 DP part, ...) of A_hi / A_lo, and the 25th (columns 48, 49) rotates among the quadrant's
                     // warps from stage to stage (a fixed owner made that warp the pace-setter of the whole CTA: pipeline
                     // trace).  The bias column (50) and the zero padding (51..55) are written once per launch.
-                    constexpr int DP = 24 / tc::kProdParts, NC = 2 * DP;   // 8 double-pairs = 16 columns, or 6 = 12
+                    // With two producer warps per quadrant (DUAL) a warp's 12 double-pairs go through the registers in two halves.
+                    constexpr int DP = 24 / PARTS, NHALF = (PARTS == 2) ? 2 : 1, DPH = DP / NHALF, NC = 2 * DPH;   // per half: 8 double-pairs = 16 columns, or 6 = 12
                     const int part = warp >> 2;
                     const bool extra = rot == part;
                     uint32_t vh[NC + 2], vl[NC + 2];
@@ -675,39 +703,29 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
                     const uint32_t slot_par = SINGLE_A ? (((n - 1) >> 1) & 1) : ((use & 1) ^ 1);
                     bool slot_ready = false;
                     // (the overflow clamps of the 100 exponents are skipped when every lane's |y| is below the launch's bound)
-                    auto compute_stage = [&](auto clamp_c) {
+                    auto compute_half = [&](auto clamp_c, auto hf_c) {
                     constexpr bool CL = decltype(clamp_c)::value;
+                    constexpr int HF = decltype(hf_c)::value;
 #pragma unroll
-                    for (int i = 0; i < DP; i++) {
+                    for (int i = 0; i < DPH; i++) {
 #if MVN_TC_EXPERIMENT == 4   // bound-finding build (wrong results): half of the sigmoids
                         if (i & 1) { vh[2 * i] = vh[2 * i - 2]; vh[2 * i + 1] = vh[2 * i - 1]; vl[2 * i] = vl[2 * i - 2]; vl[2 * i + 1] = vl[2 * i - 1]; continue; }
 #endif
                         // (fetching the next stage's sample here as well measured the same and cost a spill)
-                        if (MVN_TC_EARLY_PROBE && i == DP / 2) slot_ready = tc::mbar_test(slot_bar, slot_par);
-                        if (MVN_TC_LATE_PUBLISH && i == 0) {
+                        if (MVN_TC_EARLY_PROBE && HF == 0 && i == DPH / 2) slot_ready = tc::mbar_test(slot_bar, slot_par);
+                        if (MVN_TC_LATE_PUBLISH && HF == 0 && i == 0) {
                             uint32_t th[2], tl[2];   // vh / vl may still be read by the stores of the previous stage
                             tc::compute_dpair<CL>(sP_addr, DP * part, yy, th, tl);
                             if (pending) publish();
                             vh[0] = th[0], vh[1] = th[1], vl[0] = tl[0], vl[1] = tl[1];
                             continue;
                         }
-                        tc::compute_dpair<CL>(sP_addr, DP * part + i, yy, vh + 2 * i, vl + 2 * i);
+                        tc::compute_dpair<CL>(sP_addr, DP * part + DPH * HF + i, yy, vh + 2 * i, vl + 2 * i);
                     }
-                    if (extra) tc::compute_dpair<CL>(sP_addr, 24, yy, vh + NC, vl + NC);
+                    if (HF == NHALF - 1 && extra) tc::compute_dpair<CL>(sP_addr, 24, yy, vh + NC, vl + NC);
                     };
-                    if (MVN_TC_CLAMP_FREE && __all_sync(0xffffffffu, fabsf(yv) <= y_safe)) compute_stage(std::false_type{});
-                    else compute_stage(std::true_type{});
-                    TC_TRACE(1, tid == 0);
-                    // (128 / 256 states are bound by the consumers: there the producers park instead of polling, which
-                    //  would take issue slots from the consumer warp on their scheduler)
-                    // DEC: the A columns are free once the layer-2 MMAs of the slot's previous use have read them (d_full);
-                    // round-1 layout: once the consumers have released the slot (h2 lives in the A columns)
-                    if (!slot_ready) tc::mbar_wait<(MVN_PROD_PARK || L >= MVN_TC_PARK_MINL)>(slot_bar, slot_par, timeout_flag);
-                    TC_TRACE(28, tid == 0);
-                    asm volatile("tcgen05.fence::after_thread_sync;");
-                    TC_TRACE(2, tid == 0);
-                    {
-                        const uint32_t ah = a_lane + NC * part, al = a_lane + tc::kACols + NC * part;
+                    auto store_half = [&](int hf) {
+                        const uint32_t ah = a_lane + 2 * DP * part + NC * hf, al = ah + tc::kACols;
                         if constexpr (NC == 16) {
                             tc::tmem_st16p(ah, vh);
                             tc::tmem_st16p(al, vl);
@@ -717,12 +735,31 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
                             tc::tmem_st4(ah + 8, vh + 8);
                             tc::tmem_st4(al + 8, vl + 8);
                         }
-                        if (extra) {
+                        if (hf == NHALF - 1 && extra) {
                             tc::tmem_st2(a_lane + 48, vh[NC], vh[NC + 1]);
                             tc::tmem_st2(a_lane + tc::kACols + 48, vl[NC], vl[NC + 1]);
                         }
+                    };
+                    const bool clamp_free = MVN_TC_CLAMP_FREE && __all_sync(0xffffffffu, fabsf(yv) <= y_safe);
+                    if (clamp_free) compute_half(std::false_type{}, std::integral_constant<int, 0>{});
+                    else compute_half(std::true_type{}, std::integral_constant<int, 0>{});
+                    TC_TRACE(1, tid == 0);
+                    // (128 / 256 states are bound by the consumers: there the producers park instead of polling, which
+                    //  would take issue slots from the consumer warp on their scheduler)
+                    // DEC: the A columns are free once the layer-2 MMAs of the slot's previous use have read them (d_full);
+                    // round-1 layout: once the consumers have released the slot (h2 lives in the A columns)
+                    if (!slot_ready) tc::mbar_wait<(MVN_PROD_PARK || L >= MVN_TC_PARK_MINL)>(slot_bar, slot_par, timeout_flag);
+                    TC_TRACE(28, tid == 0);
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+                    TC_TRACE(2, tid == 0);
+                    store_half(0);
+                    if constexpr (NHALF == 2) {
+                        asm volatile("tcgen05.wait::st.sync.aligned;");   // the registers of the first half are free again
+                        if (clamp_free) compute_half(std::false_type{}, std::integral_constant<int, NHALF - 1>{});
+                        else compute_half(std::true_type{}, std::integral_constant<int, NHALF - 1>{});
+                        store_half(1);
                     }
-                    rot = rot == tc::kProdParts - 1 ? 0 : rot + 1;
+                    rot = rot == PARTS - 1 ? 0 : rot + 1;
                     TC_TRACE(29, tid == 0);
                     if constexpr (MVN_TC_LATE_PUBLISH) {
                         pending = true;
@@ -805,16 +842,16 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
                 for (int tt = 0; tt < t_end; tt++, n++) {
                     const uint32_t slot = n & 1, use = n >> 1;
                     const uint32_t ts = tmem + LY::d_col(slot), slot_lane = ts + lane_base;
-                    TC_TRACE(6, warp == tc::kProdWarps && lane == 0);
+                    TC_TRACE(6, warp == PW && lane == 0);
                     tc::mbar_wait<MVN_CONS_PARK>(smem_addr(&d_full[slot]), use & 1, timeout_flag);
                     asm volatile("tcgen05.fence::after_thread_sync;");
-                    TC_TRACE(7, warp == tc::kProdWarps && lane == 0);
+                    TC_TRACE(7, warp == PW && lane == 0);
                     if (active) tc::h2_to_tmem<LAYM>(slot_lane);
                     asm volatile("tcgen05.fence::before_thread_sync;");
-                    TC_TRACE(8, warp == tc::kProdWarps && lane == 0);
+                    TC_TRACE(8, warp == PW && lane == 0);
                     asm volatile("bar.sync 2, %0;" ::"n"(32 * tc::kConvWarps));
-                    TC_TRACE(9, warp == tc::kProdWarps && lane == 0);
-                    if (warp == tc::kProdWarps + (tc::kMmaWarps > 1 ? int((n + 2) & 3) : 1) && tc::elect_one()) {  // one thread issues layer 3
+                    TC_TRACE(9, warp == PW && lane == 0);
+                    if (warp == PW + (tc::kMmaWarps > 1 ? int((n + 2) & 3) : 1) && tc::elect_one()) {  // one thread issues layer 3
                         asm volatile("tcgen05.fence::after_thread_sync;");
                         if constexpr (!MERGED) {   // 4 + 4 MMAs
 #pragma unroll
@@ -831,7 +868,7 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
                         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                             smem_addr(&d2_full[slot])));
                     }
-                    TC_TRACE(10, warp == tc::kProdWarps && lane == 0);
+                    TC_TRACE(10, warp == PW && lane == 0);
                     __syncwarp();
                 }
             }
@@ -850,11 +887,26 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
         SurvStore<L> surv;
         if constexpr (MLSE) surv.init(reinterpret_cast<uint32_t *>(after_w3) + size_t(quad) * p.surv_words * 32, lane);
         ErrAcc acc;
-        constexpr int kConsFirst = tc::kProdWarps + tc::kConvWarps;
+        constexpr int kConsFirst = PW + tc::kConvWarps;
+        // DUAL: warps kConsFirst + q (lead) and kConsFirst + 4 + q serve quadrant q.  The lead decides, emits and counts; both
+        // run the add-compare-select of their half of every layer-3 pass's chunks on the shared metrics, meet at a named
+        // barrier of their own once per stage, and the lead folds the other warp's even / odd minima into its own.
+        const bool lead = !DUAL || warp < kConsFirst + 4;
+        constexpr int NCHp = NCH / NPASS;   // chunks per layer-3 pass
+        auto pair_sync = [&]() {
+            if constexpr (DUAL) asm volatile("bar.sync %0, 64;" ::"r"(4 + quad) : "memory");
+        };
         for (int64_t ct = blockIdx.x; ct < n_cta_tiles; ct += gridDim.x) {
             const int64_t row0 = (ct * kQ + quad) * 32;
             const int64_t b = row0 + lane;
-            if (active) tr.reset();
+            if constexpr (DUAL) {
+                pair_sync();                 // the other warp is done with the previous tile's metrics
+                if (lead) tr.reset();
+                else tr.ne = tr.no = 3.0e38f;
+                pair_sync();
+            } else {
+                if (active) tr.reset();
+            }
             unsigned frame_bit_errs = 0;
             auto emit = [&](int t0, uint32_t bits) {
                 if (p.decoded) {
@@ -881,7 +933,7 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
                     const uint32_t slot = n & 1, use = n >> 1;
                     const uint32_t ts = tmem + LY::d_col(slot), slot_lane = ts + lane_base;
                     if constexpr (!MLSE) {
-                        if (active) bits |= tr.decide() << tt;   // metrics entering this stage; overlaps the wait
+                        if (active && lead) bits |= tr.decide() << tt;   // metrics entering this stage; overlaps the wait
                     }
                     tc::mbar_wait<MVN_CONS_PARK>(smem_addr(&d2_full[slot]), (NPASS * use) & 1, timeout_flag);
                     asm volatile("tcgen05.fence::after_thread_sync;");
@@ -891,7 +943,7 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
                     // 16 source states per chunk: priors = D_main + D_corr / 2048, cost = -prior (vnet_detector.py:57)
                     auto chunk = [&](auto cc) {
                         constexpr int c = decltype(cc)::value;
-                        constexpr bool last = (c == NCH - 1);
+                        constexpr bool last = (c == NCH - 1) || (DUAL && c == NCH - NCHp / 2 - 1);   // this warp's last tcgen05.ld of the stage
                         constexpr int col = 16 * (c % (NCH / NPASS));   // a pass refills the same D columns
                         float pm_[16], pc_[16];
                         if (active) {
@@ -920,12 +972,17 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
                             for (int i = 0; i < C; i++) dst[c * C + i] = pr[i];
                         }
                     };
-                    tc::static_for<0, NCH / NPASS>(chunk);
+                    if constexpr (!DUAL) {
+                        tc::static_for<0, NCHp>(chunk);
+                    } else {
+                        if (lead) tc::static_for<0, NCHp / 2>(chunk);
+                        else tc::static_for<NCHp / 2, NCHp>(chunk);
+                    }
                     if constexpr (NPASS == 2) {
                         // every consumer warp has read the first half of the priors: one thread issues the second layer-3 pass
                         // into the same columns (h2 is still in the slot's A columns), then all wait for it
                         asm volatile("tcgen05.fence::before_thread_sync;");
-                        asm volatile("bar.sync 3, %0;" ::"n"(32 * tc::kConsWarps));
+                        asm volatile("bar.sync 3, %0;" ::"n"(32 * KW));
                         if (warp == kConsFirst && tc::elect_one()) {
                             asm volatile("tcgen05.fence::after_thread_sync;");
                             issue_layer3_merged(ts, 1);
@@ -935,7 +992,24 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
                         __syncwarp();
                         tc::mbar_wait<MVN_CONS_PARK>(smem_addr(&d2_full[slot]), (NPASS * use + 1) & 1, timeout_flag);
                         asm volatile("tcgen05.fence::after_thread_sync;");
-                        tc::static_for<NCH / NPASS, NCH>(chunk);
+                        if constexpr (!DUAL) {
+                            tc::static_for<NCHp, NCH>(chunk);
+                        } else {
+                            if (lead) tc::static_for<NCHp, NCHp + NCHp / 2>(chunk);
+                            else tc::static_for<NCHp + NCHp / 2, NCH>(chunk);
+                        }
+                    }
+                    if constexpr (DUAL) {
+                        float *xc = cons_xchg + (n & 1) * (2 * 32 * kQ) + quad * 32 + lane;
+                        if (!lead) {
+                            xc[0] = tr.ne;
+                            xc[32 * kQ] = tr.no;
+                        }
+                        pair_sync();             // both halves of the new metrics are written, the old ones read
+                        if (lead) {
+                            tr.ne = fminf(tr.ne, xc[0]);
+                            tr.no = fminf(tr.no, xc[32 * kQ]);
+                        }
                     }
                     if (active) tr.commit();
                     if constexpr (MLSE) surv.put(t0 + tt, sv, t0 + tt == p.n_stages - 1);
@@ -943,7 +1017,7 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
                 }
                 __syncwarp();
                 if constexpr (!MLSE) {
-                    if (active) emit(t0, bits);
+                    if (active && lead) emit(t0, bits);
                 }
             }
             if constexpr (MLSE) {
@@ -954,7 +1028,7 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
                 __syncwarp();
             }
             if (p.target) {
-                const bool counted = active && b < p.B && !(p.pilot_period > 0 && b % p.pilot_period == 0);
+                const bool counted = active && lead && b < p.B && !(p.pilot_period > 0 && b % p.pilot_period == 0);
                 if (counted) {
                     acc.bit_errs += frame_bit_errs;
                     acc.frame_errs += frame_bit_errs ? 1u : 0u;
@@ -973,7 +1047,7 @@ __global__ void __maxnreg__(tc::kProdWarps == 16 ? 72 : 80) vnet_decode_tc_kerne
 template <int L>
 constexpr size_t tc_smem_bytes() {   // + the consumers' survivor masks in MLSE mode (launch_tc)
     constexpr int kQ = 4;
-    return size_t(tc::kBBytes) + tc::b2_bytes(1 << L) + (size_t(L == 8 ? 0 : (tc::kProdParts + 1) * kQ) * kTileFloats + 4 * (tc::kK / 2)) * sizeof(float) +
+    return size_t(tc::kBBytes) + tc::b2_bytes(1 << L) + (size_t(L == 8 ? 0 : (tc::Roles<L>::PARTS + 1) * kQ) * kTileFloats + 4 * (tc::kK / 2)) * sizeof(float) +
            (L > 5 ? SmemTrellis<L>::bytes(32 * kQ) : 0);
 }
 
